@@ -254,7 +254,8 @@ def shearlayer_2d(Nx: int = 319, Ny: int = 159, Nt: int = 100) -> Dict:
 
 
 def shockbubble_3d(nc: int = 64, Nt: int = 10, ncx: int | None = None, ncy: int | None = None,
-                   ncz: int | None = None, periodic_z: bool = False, z_invariant: bool = False) -> Dict:
+                   ncz: int | None = None, periodic_z: bool = False, z_invariant: bool = False,
+                   smooth: bool = True) -> Dict:
     """EXTENSION (no reference): the 2D_shockbubble fluids and states on a cube [-0.5,0.5]^3
     of ncx x ncy x ncz cells, the helium circle extruded to a sphere (BASELINE config 5:
     512^3 per GPU).  z_invariant=True keeps the 2-D cylinder (for the 3-D-vs-2-D cross-check)."""
@@ -284,6 +285,11 @@ def shockbubble_3d(nc: int = 64, Nt: int = 10, ncx: int | None = None, ncy: int 
     p3 = dict(base, geometry=(10 if z_invariant else 8), x_centroid=0., radius=leng / 5.)
     p3.update({'vel(1)': 0., 'pres': 101325., 'alpha_rho(1)': 0.0, 'alpha_rho(2)': 0.167, 'alpha(1)': 0.0, 'alpha(2)': 1.0,
                'alter_patch(1)': 'T'})
+    if smooth:
+        # a sharp sphere always has 1-2 cell wide chords near its caps, where component-wise
+        # WENO5 of (1.29 -> 0) and (0 -> 0.167) undershoots to a negative mixture density;
+        # smear the interface over a few cells as 3-D MFC cases customarily do
+        p3.update({'smoothen': 'T', 'smooth_patch_id': 1, 'smooth_coeff': 0.5})
     for i, pt in enumerate((p1, p2, p3), start=1):
         for k, v in pt.items():
             d[f'patch_icpp({i})%{k}'] = v

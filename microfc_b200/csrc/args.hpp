@@ -1,0 +1,82 @@
+// args.hpp -- kernel argument blocks and the launcher table shared by the API and the two
+// kernel builds (fast / strict).
+#pragma once
+#include <cuda_runtime.h>
+#include "layout.hpp"
+
+namespace mfc {
+
+struct SweepArgs {
+    GridDesc g;
+    const double *q;       // stage state, conservative (alpha_rho, mom, E, alpha), ghosts filled
+    const double *prim;    // velocity (nd fields) + pressure of the stage state, ghosted
+    double *rhs;           // accumulated RHS (same padded layout)
+    const double *q1;      // q_cons_ts(1) for the fused RK update
+    double *qout;          // updated state
+    const double *coef;    // kNumWenoCoef arrays of clen doubles for this direction
+    const double *rds;     // 1/ds(-b:N+b) of this direction
+    int clen, coef_lo;     // coefficient arrays cover cells coef_lo .. coef_lo+clen-1
+    double eps, dt;
+    double gammas[kMaxFluids], pi_infs[kMaxFluids];
+    int bc_beg, bc_end;    // boundary codes of this direction (Riemann-state extrapolation, -4)
+    int first_dir;         // 1: RHS assigned (m_rhs.fpp:567-576), 0: accumulated (:610-620)
+    int rk_mode;           // 0: store RHS; 1..4: fused update, see rk_apply()
+    int seg;               // cells per thread along the sweep (march kernels)
+    int rows;              // rows per block (x kernel)
+};
+
+struct BcArgs {
+    GridDesc g;
+    double *q;
+    int dir, E, mom_normal;
+    int bc_beg, bc_end;    // only sides with a negative (physical) code are filled
+};
+
+struct HaloArgs {
+    GridDesc g;
+    double *q;
+    double *buf;
+    int dir, side, E;      // pack: side 0 = first b interior layers, 1 = last b;  unpack: ghosts at beg / end
+};
+
+struct PrimArgs {
+    GridDesc g;
+    const double *q;
+    double *prim;
+    double gammas[kMaxFluids], pi_infs[kMaxFluids];
+};
+
+struct StabArgs {
+    GridDesc g;
+    const double *q, *prim;
+    const double *ds[3];   // ds(-b:N+b) per direction
+    double gammas[kMaxFluids], pi_infs[kMaxFluids];
+    double Res[2][kMaxFluids];
+    int Re_idx[2][kMaxFluids], Re_size[2];
+    double dt;
+    unsigned long long *out;   // [0] icfl max, [1] vcfl max, [2] Rc min  as ordered bit patterns
+};
+
+// number of (transverse x layer) elements of one variable in a ghost slab of direction dir:
+// earlier directions ghosted, later ones interior only (m_rhs.fpp:696-697 vs :811-812)
+MFC_HD long long slab_count(const GridDesc &g, int dir) {
+    long long n0, n1;
+    if (dir == 0) { n0 = g.N[1] + 1; n1 = g.N[2] + 1; }
+    else if (dir == 1) { n0 = g.N[0] + 1 + 2*g.b; n1 = g.N[2] + 1; }
+    else { n0 = g.N[0] + 1 + 2*g.b; n1 = g.N[1] + 1 + 2*g.b; }
+    return n0*n1*g.b;
+}
+
+// every launcher returns the number of kernels it launched (0 = unsupported combination)
+struct Launchers {
+    int (*sweep)(int nf, int nd, int dir, const SweepArgs &, cudaStream_t);
+    int (*prim)(int nf, int nd, const PrimArgs &, cudaStream_t);
+    int (*bc)(const BcArgs &, cudaStream_t);
+    int (*halo_pack)(const HaloArgs &, cudaStream_t);
+    int (*halo_unpack)(const HaloArgs &, cudaStream_t);
+    int (*stability)(int nf, int nd, const StabArgs &, cudaStream_t);
+};
+const Launchers &launchers_fast();
+const Launchers &launchers_strict();
+
+}  // namespace mfc

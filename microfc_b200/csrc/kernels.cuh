@@ -1,0 +1,502 @@
+// kernels.cuh -- hand-written FP64 CUDA kernels (sm_100a) for the s_compute_rhs pipeline and
+// the fused TVD-RK update.  No tensor cores: this is a stencil, not a dense contraction.
+//
+// Compiled twice (kernels_fast.cu / kernels_strict.cu):
+//   MFC_STRICT=0  namespace mfc_fast    default FMA contraction, WENO weights in the
+//                                       one-division product form (see weno5())
+//   MFC_STRICT=1  namespace mfc_strict  -fmad=false and the reference's exact operation
+//                                       order: bit-comparable with a strict CPU build
+//
+// Stage map (reference file:line -> kernel), all citations relative to /root/reference:
+//   m_rhs.fpp:686-908 ghost fill (physical BCs)              -> k_bc
+//   m_mpi_proxy.fpp:490-499,592-601 (+y) pack / unpack       -> k_halo_pack / k_halo_unpack
+//   m_variables_conversion.fpp:313-375 cons -> prim          -> k_prim
+//   m_weno.fpp:470-535 + m_riemann_solvers.fpp:132-327 +
+//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_sweep_x (warp-shuffle pencil)
+//                                                               k_sweep_march (y / z pencils)
+//   m_data_output.fpp:197-258 stability criteria             -> k_stability
+#pragma once
+#include <cuda_runtime.h>
+#include "args.hpp"
+
+#ifndef MFC_STRICT
+#define MFC_STRICT 0
+#endif
+#if MFC_STRICT
+#define MFC_NS mfc_strict
+#else
+#define MFC_NS mfc_fast
+#endif
+
+namespace MFC_NS {
+
+using namespace mfc;
+
+// ------------------------------------------------------------------------------------------
+// RK update, m_time_steppers.fpp -- the operand order of each statement is kept
+//   1: q1 + dt*rhs                      (:167-169, :227-229, :302-304)
+//   2: (q1 + q2 + dt*rhs)/2             (:245-248)
+//   3: (3*q1 + q2 + dt*rhs)/4           (:322-325)
+//   4: (q1 + 2*q2 + 2*dt*rhs)/3         (:342-345)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rk_apply(int mode, double q1, double qs, double rhs, double dt) {
+    switch (mode) {
+    case 1: return q1 + dt*rhs;
+    case 2: return (q1 + qs + dt*rhs)/2.0;
+    case 3: return (3.0*q1 + qs + dt*rhs)/4.0;
+    default: return (q1 + 2.0*qs + 2.0*dt*rhs)/3.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// WENO5-JS on one 5-cell stencil v[0..4] = v(j-2..j+2), m_weno.fpp:476-531.
+// c[] = the 27 grid-dependent coefficients of cell j:
+//   c[0..5]  poly_coef_cbL(j,k,q) k-major    c[6..11] poly_coef_cbR
+//   c[12..14] d_cbL(k,j)   c[15..17] d_cbR(k,j)   c[18..26] beta_coef(j,k,q) k-major
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void weno5(const double v[5], const double c[27], double eps, double &vL, double &vR) {
+    const double dvd1 = v[4] - v[3];                                   // :476-483
+    const double dvd0 = v[3] - v[2];
+    const double dvdm1 = v[2] - v[1];
+    const double dvdm2 = v[1] - v[0];
+    double pl0 = v[2] + c[0]*dvd1 + c[1]*dvd0;                         // :485-493
+    double pl1 = v[2] + c[2]*dvd0 + c[3]*dvdm1;
+    double pl2 = v[2] + c[4]*dvdm1 + c[5]*dvdm2;
+    double pr0 = v[2] + c[6]*dvd1 + c[7]*dvd0;                         // :516-524
+    double pr1 = v[2] + c[8]*dvd0 + c[9]*dvdm1;
+    double pr2 = v[2] + c[10]*dvdm1 + c[11]*dvdm2;
+#if MFC_STRICT
+    const double b0 = c[18]*dvd1*dvd1 + c[19]*dvd1*dvd0 + c[20]*dvd0*dvd0 + eps;          // :495-506
+    const double b1 = c[21]*dvd0*dvd0 + c[22]*dvd0*dvdm1 + c[23]*dvdm1*dvdm1 + eps;
+    const double b2 = c[24]*dvdm1*dvdm1 + c[25]*dvdm1*dvdm2 + c[26]*dvdm2*dvdm2 + eps;
+    double a0 = c[12]/(b0*b0), a1 = c[13]/(b1*b1), a2 = c[14]/(b2*b2);                    // :508
+    double s = a0 + a1 + a2;
+    double w0 = a0/s, w1 = a1/s, w2 = a2/s;                                                // :510
+    vL = w0*pl0 + w1*pl1 + w2*pl2;                                                         // :514
+    a0 = c[15]/(b0*b0); a1 = c[16]/(b1*b1); a2 = c[17]/(b2*b2);                            // :526
+    s = a0 + a1 + a2;
+    w0 = a0/s; w1 = a1/s; w2 = a2/s;                                                       // :528
+    vR = w0*pr0 + w1*pr1 + w2*pr2;                                                         // :531
+#else
+    // Same weights, algebraically: omega_k = (d_k/beta_k^2)/sum_l(d_l/beta_l^2).  Multiplying
+    // numerator and denominator by (beta_0 beta_1 beta_2)^2 gives
+    //   omega_k = d_k B_k / sum_l d_l B_l,   B_k = prod_{l != k} beta_l^2,
+    // and the two face values share ONE division:  vL = NL*DR/(DL*DR), vR = NR*DL/(DL*DR).
+    // 12 FP64 divisions per reconstruction become 1; rounding differs at the 1e-16 level.
+    const double p11 = dvd1*dvd1, p10 = dvd1*dvd0, p00 = dvd0*dvd0, p0m = dvd0*dvdm1,
+                 pmm = dvdm1*dvdm1, pm2 = dvdm1*dvdm2, p22 = dvdm2*dvdm2;
+    const double b0 = fma(c[18], p11, fma(c[19], p10, fma(c[20], p00, eps)));
+    const double b1 = fma(c[21], p00, fma(c[22], p0m, fma(c[23], pmm, eps)));
+    const double b2 = fma(c[24], pmm, fma(c[25], pm2, fma(c[26], p22, eps)));
+    const double q0 = b0*b0, q1 = b1*b1, q2 = b2*b2;
+    const double B0 = q1*q2, B1 = q0*q2, B2 = q0*q1;
+    const double aL0 = c[12]*B0, aL1 = c[13]*B1, aL2 = c[14]*B2;
+    const double aR0 = c[15]*B0, aR1 = c[16]*B1, aR2 = c[17]*B2;
+    const double DL = aL0 + aL1 + aL2, DR = aR0 + aR1 + aR2;
+    const double NL = fma(aL0, pl0, fma(aL1, pl1, aL2*pl2));
+    const double NR = fma(aR0, pr0, fma(aR1, pr1, aR2*pr2));
+    const double inv = 1.0/(DL*DR);
+    vL = NL*(DR*inv);
+    vR = NR*(DL*inv);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// HLLC flux at one face, m_riemann_solvers.fpp:136-325.  L/R are the reconstructed primitive
+// states [alpha_rho(NF) | vel(ND) | pres | alpha(NF)] left and right of the face; NRM is the
+// sweep direction (dir_idx(1), :464-470).  dir_flg is folded in exactly: it is 0 or 1, and
+// 1*x + 0*y == x for finite y.
+//   F[E]  : flux_rs*_vf          uf : vel_src_rs*_vf(normal) = flux_src_rs*_vf(advxb) (:325)
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND, int NRM>
+__device__ __forceinline__ void hllc(const double *L, const double *R, const double *gam, const double *pinf,
+                                     double *F, double &uf) {
+    constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+    double vel_L_rms = 0.0, vel_R_rms = 0.0;                            // :138-145
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        vel_L_rms = vel_L_rms + L[MOM + i]*L[MOM + i];
+        vel_R_rms = vel_R_rms + R[MOM + i]*R[MOM + i];
+    }
+    const double pres_L = L[EN], pres_R = R[EN];                        // :147-148
+    double rho_L = 0.0, gamma_L = 0.0, pi_inf_L = 0.0, rho_R = 0.0, gamma_R = 0.0, pi_inf_R = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {                                      // :159-167
+        rho_L = rho_L + L[i];
+        gamma_L = gamma_L + L[ADV + i]*gam[i];
+        pi_inf_L = pi_inf_L + L[ADV + i]*pinf[i];
+        rho_R = rho_R + R[i];
+        gamma_R = gamma_R + R[ADV + i]*gam[i];
+        pi_inf_R = pi_inf_R + R[ADV + i]*pinf[i];
+    }
+    const double uL = L[MOM + NRM], uR = R[MOM + NRM];
+    const double E_L = gamma_L*pres_L + pi_inf_L + 5e-1*rho_L*vel_L_rms;   // :202
+    const double E_R = gamma_R*pres_R + pi_inf_R + 5e-1*rho_R*vel_R_rms;   // :204
+    const double H_L = (E_L + pres_L)/rho_L;                            // :206-207
+    const double H_R = (E_R + pres_R)/rho_R;
+    const double c_L = sqrt((H_L - 5e-1*vel_L_rms)/gamma_L);            // :220-223
+    const double c_R = sqrt((H_R - 5e-1*vel_R_rms)/gamma_R);
+    const double s_L = fmin(uL - c_L, uR - c_R);                        // :232-233
+    const double s_R = fmax(uR + c_R, uL + c_L);
+    const double s_S = (pres_R - pres_L + rho_L*uL*(s_L - uL) - rho_R*uR*(s_R - uR))   // :235-240
+                       /(rho_L*(s_L - uL) - rho_R*(s_R - uR));
+    const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);            // :245
+    const double xi_L = (s_L - uL)/(s_L - s_S);                         // :249-250
+    const double xi_R = (s_R - uR)/(s_R - s_S);
+    const double xi_M = (5e-1 + copysign(5e-1, s_S));                   // :254-255
+    const double xi_P = (5e-1 - copysign(5e-1, s_S));
+#pragma unroll
+    for (int i = 0; i < NF; i++)                                        // :258-264
+        F[i] = xi_M*L[i]*(uL + s_M*(xi_L - 1.0)) + xi_P*R[i]*(uR + s_P*(xi_R - 1.0));
+#pragma unroll
+    for (int i = 0; i < ND; i++) {                                      // :270-286
+        if (i == NRM)
+            F[MOM + i] = xi_M*(rho_L*(uL*L[MOM + i] + s_M*(xi_L*(s_S) - L[MOM + i])) + (pres_L))
+                         + xi_P*(rho_R*(uR*R[MOM + i] + s_P*(xi_R*(s_S) - R[MOM + i])) + (pres_R));
+        else
+            F[MOM + i] = xi_M*(rho_L*(uL*L[MOM + i] + s_M*(xi_L*(L[MOM + i]) - L[MOM + i])))
+                         + xi_P*(rho_R*(uR*R[MOM + i] + s_P*(xi_R*(R[MOM + i]) - R[MOM + i])));
+    }
+    F[EN] = xi_M*(uL*(E_L + pres_L)                                     // :291-299
+                  + s_M*(xi_L*(E_L + (s_S - uL)*(rho_L*s_S + pres_L/(s_L - uL))) - E_L))
+            + xi_P*(uR*(E_R + pres_R)
+                    + s_P*(xi_R*(E_R + (s_S - uR)*(rho_R*s_S + pres_R/(s_R - uR))) - E_R));
+#pragma unroll
+    for (int i = 0; i < NF; i++)                                        // :304-310
+        F[ADV + i] = xi_M*L[ADV + i]*(uL + s_M*(xi_L - 1.0)) + xi_P*R[ADV + i]*(uR + s_P*(xi_R - 1.0));
+    uf = xi_M*(uL + s_M*(xi_L - 1.0)) + xi_P*(uR + s_P*(xi_R - 1.0));   // :316-325
+}
+
+// pointer to reconstruction variable v of the stage state: partial densities and volume
+// fractions come straight from the conservative state (q_prim_qp aliases q_cons_qp there,
+// m_rhs.fpp:154-164), velocity and pressure from the prim planes.
+template <int NF, int ND>
+__device__ __forceinline__ const double *var_plane(const SweepArgs &a, int v) {
+    constexpr int MOM = NF, ADV = NF + ND + 1;
+    return (v >= MOM && v < ADV) ? a.prim + (long long)(v - MOM)*a.g.fstride : a.q + (long long)v*a.g.fstride;
+}
+
+__device__ __forceinline__ void load_coef(const SweepArgs &a, int cell, double c[27]) {
+    const double *p = a.coef + (cell - a.coef_lo);
+#pragma unroll
+    for (int i = 0; i < 27; i++) c[i] = __ldg(p + (long long)i*a.clen);
+}
+
+// RHS of one cell from its two faces (m_rhs.fpp:567-589 / :610-635) and, if requested, the
+// fused RK stage (m_time_steppers.fpp:298-348).  Fm/ufm: face s-1/2, Fp/ufp: face s+1/2.
+template <int NF, int ND>
+__device__ __forceinline__ void finish_cell(const SweepArgs &a, long long cell, double rds,
+                                            const double *Fm, double ufm, const double *Fp, double ufp) {
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1;
+    const long long fs = a.g.fstride;
+#pragma unroll
+    for (int v = 0; v < E; v++) {
+        double r = rds*(Fm[v] - Fp[v]);
+        if (!a.first_dir) r = a.rhs[v*fs + cell] + r;
+        double qs = 0.0;
+        if (v >= ADV || a.rk_mode >= 2) qs = a.q[v*fs + cell];
+        if (v >= ADV) r = r + rds*qs*(ufp - ufm);
+        if (a.rk_mode == 0) {
+            a.rhs[v*fs + cell] = r;
+        } else {
+            const double q1 = a.q1[v*fs + cell];
+            a.qout[v*fs + cell] = rk_apply(a.rk_mode, q1, qs, r, a.dt);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x sweep.  One warp owns 32 consecutive cells j0-1 .. j0+30 of a row: every lane
+// reconstructs its own cell (all E variables), the right neighbour's left-face state arrives
+// by warp shuffle, the lane solves the Riemann problem at its right face, the left face's
+// flux arrives by shuffle, and lanes 1..30 finish their cell.  30 of 32 lanes produce output
+// (6 % redundancy), no shared memory, no block barrier, loads coalesced along x.
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND>
+__global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1;
+    const GridDesc &g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j0 = (blockIdx.x*4 + warp)*30;
+    if (j0 > g.N[0]) return;                       // whole warp out of range
+    const int j_raw = j0 - 1 + lane;
+    const int j = min(j_raw, g.N[0] + 1);          // clamp loads; clamped lanes never store
+    const int l = blockIdx.z;
+    double c[27];
+    load_coef(a, j, c);
+    const double rds = a.rds[j + g.b];
+    const unsigned full = 0xffffffffu;
+    for (int r = 0; r < a.rows; r++) {
+        const int k = blockIdx.y*a.rows + r;
+        if (k > g.N[1]) break;
+        const long long cell = g.at(j, k, l);
+        double vL[E], vR[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            const double *p = var_plane<NF, ND>(a, v) + cell;
+            double s[5];
+#pragma unroll
+            for (int t = 0; t < 5; t++) s[t] = __ldg(p + (t - 2));
+            weno5(s, c, a.eps, vL[v], vR[v]);
+        }
+        // Riemann problem at face j+1/2: left state = my right-face value, right state = the
+        // next cell's left-face value (R-first call, m_rhs.fpp:545-556)
+        double Ls[E], Rs[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            Ls[v] = vR[v];
+            Rs[v] = __shfl_down_sync(full, vL[v], 1);
+        }
+        if (a.bc_beg == -4 && j_raw == -1) {       // m_riemann_solvers.fpp:480-487
+#pragma unroll
+            for (int v = 0; v < E; v++) Ls[v] = Rs[v];
+        }
+        if (a.bc_end == -4 && j_raw == g.N[0]) {   // :515-523
+#pragma unroll
+            for (int v = 0; v < E; v++) Rs[v] = Ls[v];
+        }
+        double F[E], uf;
+        hllc<NF, ND, 0>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+        double Fm[E], ufm;
+#pragma unroll
+        for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
+        ufm = __shfl_up_sync(full, uf, 1);
+        if (lane >= 1 && lane <= 30 && j_raw <= g.N[0])
+            finish_cell<NF, ND>(a, cell, rds, Fm, ufm, F, uf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// y / z sweep.  Threads are laid along x (coalesced), each thread marches a pencil of `seg`
+// cells along the sweep direction, carrying the previous cell's right-face state and the
+// previous face's flux in registers: every reconstruction and every Riemann solve is done
+// exactly once per pencil (plus two warm-up reconstructions and one warm-up face).  The
+// 5-point stencil is re-read from L1/L2 each step; only HBM-resident planes are touched,
+// no transposed copy is ever made.
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND, int DIR>
+__global__ void __launch_bounds__(128) k_sweep_march(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1;
+    const GridDesc &g = a.g;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j > g.N[0]) return;
+    const int t = blockIdx.z;                      // the remaining transverse index
+    const int s0 = blockIdx.y*a.seg;
+    const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
+    const long long ss = DIR == 1 ? g.sy : g.sz;
+    const long long base = DIR == 1 ? g.at(j, 0, t) : g.at(j, t, 0);
+    double vRp[E], Fp[E], ufp = 0.0;
+#pragma unroll
+    for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
+    for (int s = s0 - 1; s <= s1 + 1; s++) {
+        double c[27];
+        load_coef(a, s, c);
+        const long long cell = base + (long long)s*ss;
+        double vL[E], vR[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            const double *p = var_plane<NF, ND>(a, v) + cell;
+            double st[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) st[q] = __ldg(p + (long long)(q - 2)*ss);
+            weno5(st, c, a.eps, vL[v], vR[v]);
+        }
+        if (s >= s0) {
+            // face s-1/2 between cells s-1 (left state vRp) and s (right state vL)
+            double Ls[E], Rs[E];
+#pragma unroll
+            for (int v = 0; v < E; v++) { Ls[v] = vRp[v]; Rs[v] = vL[v]; }
+            if (a.bc_beg == -4 && s == 0) {
+#pragma unroll
+                for (int v = 0; v < E; v++) Ls[v] = Rs[v];
+            }
+            if (a.bc_end == -4 && s == g.N[DIR] + 1) {
+#pragma unroll
+                for (int v = 0; v < E; v++) Rs[v] = Ls[v];
+            }
+            double F[E], uf;
+            hllc<NF, ND, DIR>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+            if (s >= s0 + 1)
+                finish_cell<NF, ND>(a, cell - ss, a.rds[s - 1 + g.b], Fp, ufp, F, uf);
+#pragma unroll
+            for (int v = 0; v < E; v++) Fp[v] = F[v];
+            ufp = uf;
+        }
+#pragma unroll
+        for (int v = 0; v < E; v++) vRp[v] = vR[v];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conservative -> primitive over the ghosted box, m_variables_conversion.fpp:326-373.
+// Only velocity and pressure are stored (alpha_rho / alpha alias the conservative state).
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND>
+__global__ void __launch_bounds__(256) k_prim(const __grid_constant__ PrimArgs a) {
+    constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+    const GridDesc &g = a.g;
+    const int nx = g.N[0] + 1 + 2*g.b;
+    const int jj = blockIdx.x*blockDim.x + threadIdx.x;
+    if (jj >= nx) return;
+    const int row = blockIdx.y + g.ey*blockIdx.z;  // (k, l) incl. ghosts
+    const long long cell = (long long)(kXoff - g.b + jj) + (long long)g.pitch*row;
+    const long long fs = g.fstride;
+    double rho = 0.0, gamma = 0.0, pi_inf = 0.0;   // :187-227
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        const double al = a.q[(ADV + i)*fs + cell];
+        rho = rho + a.q[i*fs + cell];
+        gamma = gamma + al*a.gammas[i];
+        pi_inf = pi_inf + al*a.pi_infs[i];
+    }
+    rho = fmax(rho, 1e-16);                        // :353 (sgm_eps)
+    double dyn = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) {                 // :357-362
+        const double mom = a.q[(MOM + i)*fs + cell];
+        const double u = mom/rho;
+        a.prim[i*fs + cell] = u;
+        dyn = dyn + 5e-1*mom*u;
+    }
+    a.prim[ND*fs + cell] = (a.q[EN*fs + cell] - dyn - pi_inf)/gamma;   // :98-106
+}
+
+// ------------------------------------------------------------------------------------------
+// physical boundary conditions on the conservative state, one direction per launch in the
+// reference's order x, y, z so that later directions see earlier ghosts (corners),
+// m_rhs.fpp:692-797 (x), :807-905 (y).  bc <= -3: extrapolation, -2: symmetry (normal
+// momentum negated), -1: periodic.  Sides owned by a neighbour rank (bc >= 0) are left to
+// the halo exchange.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bc_decode(const GridDesc &g, int dir, long long idx, int &t0, int &t1, int &layer) {
+    // transverse extents: earlier directions ghosted, later ones interior only
+    int n0, n1, o0, o1;
+    if (dir == 0) { n0 = g.N[1] + 1; o0 = 0; n1 = g.N[2] + 1; o1 = 0; }
+    else if (dir == 1) { n0 = g.N[0] + 1 + 2*g.b; o0 = -g.b; n1 = g.N[2] + 1; o1 = 0; }
+    else { n0 = g.N[0] + 1 + 2*g.b; o0 = -g.b; n1 = g.N[1] + 1 + 2*g.b; o1 = -g.b; }
+    t0 = (int)(idx % n0) + o0; idx /= n0;
+    t1 = (int)(idx % n1) + o1; idx /= n1;
+    layer = (int)idx;                              // 0 .. b-1
+}
+__device__ __forceinline__ long long bc_cell(const GridDesc &g, int dir, int s, int t0, int t1) {
+    return dir == 0 ? g.at(s, t0, t1) : (dir == 1 ? g.at(t0, s, t1) : g.at(t0, t1, s));
+}
+
+__global__ void __launch_bounds__(256) k_bc(const __grid_constant__ BcArgs a) {
+    const GridDesc &g = a.g;
+    const long long n = slab_count(g, a.dir);
+    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int v = blockIdx.y, side = blockIdx.z;
+    const int code = side == 0 ? a.bc_beg : a.bc_end;
+    if (code >= 0) return;
+    int t0, t1, layer;
+    bc_decode(g, a.dir, idx, t0, t1, layer);
+    const int jj = layer + 1, N = g.N[a.dir];      // ghost index -jj or N+jj
+    int src;
+    if (code <= -3) src = side == 0 ? 0 : N;                       // :698-699,:750-751
+    else if (code == -2) src = side == 0 ? jj - 1 : N - (jj - 1);  // :711-720,:764-774
+    else src = side == 0 ? N - (jj - 1) : jj - 1;                  // :731-732,:786-787
+    const int dst = side == 0 ? -jj : N + jj;
+    double *f = a.q + (long long)v*g.fstride;
+    double val = f[bc_cell(g, a.dir, src, t0, t1)];
+    if (code == -2 && v == a.mom_normal) val = -val;               // :715-716,:829-830
+    f[bc_cell(g, a.dir, dst, t0, t1)] = val;
+}
+
+// halo pack / unpack (m_mpi_proxy.fpp:490-499,539-548,592-601 and the y blocks).  The wire
+// layout is private to this library (t0 fastest, then t1, layer, variable), chosen so both
+// sides stream along x.
+__global__ void __launch_bounds__(256) k_halo_pack(const __grid_constant__ HaloArgs a) {
+    const GridDesc &g = a.g;
+    const long long n = slab_count(g, a.dir);
+    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int v = blockIdx.y;
+    int t0, t1, layer;
+    bc_decode(g, a.dir, idx, t0, t1, layer);
+    const int N = g.N[a.dir];
+    const int src = a.side == 0 ? layer : N - g.b + 1 + layer;     // first b / last b interior layers
+    a.buf[(long long)v*n + idx] = a.q[(long long)v*g.fstride + bc_cell(g, a.dir, src, t0, t1)];
+}
+__global__ void __launch_bounds__(256) k_halo_unpack(const __grid_constant__ HaloArgs a) {
+    const GridDesc &g = a.g;
+    const long long n = slab_count(g, a.dir);
+    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int v = blockIdx.y;
+    int t0, t1, layer;
+    bc_decode(g, a.dir, idx, t0, t1, layer);
+    const int N = g.N[a.dir];
+    const int dst = a.side == 0 ? -g.b + layer : N + 1 + layer;    // ghost layers in ascending order
+    a.q[(long long)v*g.fstride + bc_cell(g, a.dir, dst, t0, t1)] = a.buf[(long long)v*n + idx];
+}
+
+// ------------------------------------------------------------------------------------------
+// stability criteria, m_data_output.fpp:197-258: per-cell ICFL (+VCFL, Rc when viscous), warp
+// shuffle reduction, one atomic per block on the ordered bit pattern (all values are >= 0).
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND>
+__global__ void __launch_bounds__(256) k_stability(const __grid_constant__ StabArgs a) {
+    constexpr int ADV = NF + ND + 1;
+    const GridDesc &g = a.g;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    const int k = blockIdx.y, l = blockIdx.z;
+    double icfl = 0.0, vcfl = 0.0, Rc = 1.0e300;
+    const bool visc = a.Re_size[0] > 0 || a.Re_size[1] > 0;
+    if (j <= g.N[0]) {
+        const long long cell = g.at(j, k, l), fs = g.fstride;
+        double rho = 0.0, gamma = 0.0, pi_inf = 0.0, al[NF];
+#pragma unroll
+        for (int i = 0; i < NF; i++) {
+            al[i] = a.q[(ADV + i)*fs + cell];
+            rho = rho + a.q[i*fs + cell];
+            gamma = gamma + al[i]*a.gammas[i];
+            pi_inf = pi_inf + al[i]*a.pi_infs[i];
+        }
+        double vel[ND];
+#pragma unroll
+        for (int i = 0; i < ND; i++) vel[i] = a.prim[i*fs + cell];
+        const double pres = a.prim[ND*fs + cell];
+        const double c = sqrt(((gamma + 1.0)*pres + pi_inf)/(gamma*rho));        // :215-216
+        const double dx = a.ds[0][j + g.b];
+        double Re[2] = {0.0, 0.0};
+        if (visc) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                double r = a.Re_size[i] > 0 ? 0.0 : -1e6;
+                for (int q = 0; q < a.Re_size[i]; q++) r = al[a.Re_idx[i][q]]/a.Res[i][q] + r;
+                Re[i] = 1.0/fmax(r, 1e-16);
+            }
+        }
+        if (ND == 1) {                                                           // :231-241
+            icfl = (a.dt/dx)*(fabs(vel[0]) + c);
+            if (visc) { vcfl = fmax(a.dt/Re[0], a.dt/Re[1])/(dx*dx); Rc = dx*(fabs(vel[0]) + c)/fmax(1.0/Re[0], 1.0/Re[1]); }
+        } else {
+            const double dy = a.ds[1][k + g.b];
+            double mn = fmin(dx/(fabs(vel[0]) + c), dy/(fabs(vel[ND > 1 ? 1 : 0]) + c));   // :220-221
+            if (ND == 3) mn = fmin(mn, a.ds[2][l + g.b]/(fabs(vel[ND > 2 ? 2 : 0]) + c));
+            icfl = a.dt/mn;
+            if (visc) {                                                          // :223-229
+                const double md = fmin(dx, dy);
+                vcfl = fmax(a.dt/Re[0], a.dt/Re[1])/(md*md);
+                Rc = fmin(dx*(fabs(vel[0]) + c), dy*(fabs(vel[ND > 1 ? 1 : 0]) + c))/fmax(1.0/Re[0], 1.0/Re[1]);
+            }
+        }
+    }
+    unsigned long long bi = (unsigned long long)__double_as_longlong(icfl);
+    unsigned long long bv = (unsigned long long)__double_as_longlong(vcfl);
+    unsigned long long br = (unsigned long long)__double_as_longlong(Rc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bi = max(bi, __shfl_xor_sync(0xffffffffu, bi, o));
+        bv = max(bv, __shfl_xor_sync(0xffffffffu, bv, o));
+        br = min(br, __shfl_xor_sync(0xffffffffu, br, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(a.out + 0, bi);
+        if (visc) { atomicMax(a.out + 1, bv); atomicMin(a.out + 2, br); }
+    }
+}
+
+}  // namespace MFC_NS

@@ -1,0 +1,551 @@
+// mfc_api.cu -- the C ABI of libmfc_b200.so (include/mfc_b200.h): device state, stage
+// orchestration (s_compute_rhs, m_rhs.fpp:405-679, and the TVD-RK steppers,
+// m_time_steppers.fpp:129-362), NCCL halo exchange (replacing m_mpi_proxy.fpp:468-979) and
+// the stability reduction (m_data_output.fpp:249-274, m_mpi_common.fpp:135-171).
+//
+// There is NO CPU fallback: without a usable CUDA device every entry fails with
+// MFC_B200_ENODEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mfc_b200.h"
+#include "args.hpp"
+#include "weno_coefficients.hpp"
+
+using namespace mfc;
+
+namespace {
+
+enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_COUNT };
+const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_sweep_x", "k_sweep_march<y>", "k_sweep_march<z>",
+                                      "k_stability", "k_halo_pack", "k_halo_unpack"};
+
+// NCCL is resolved at run time so the library loads (and every symbol is exported) on hosts
+// without it; only mfc_b200_comm_init needs it.  In a process that already imported torch
+// the loader hands back torch's bundled libnccl.so.2.
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define MFC_SYM(name) *(void **)(&name) = dlsym(h, "nccl" #name); if (!name) { err = "missing NCCL symbol nccl" #name; return false; }
+        MFC_SYM(GetUniqueId) MFC_SYM(CommInitRank) MFC_SYM(CommDestroy) MFC_SYM(Send) MFC_SYM(Recv)
+        MFC_SYM(AllReduce) MFC_SYM(GroupStart) MFC_SYM(GroupEnd) MFC_SYM(GetErrorString)
+#undef MFC_SYM
+        return true;
+    }
+};
+
+struct ProfRec { int kc; cudaEvent_t a, b; };
+
+struct Sim {
+    bool inited = false, uploaded = false;
+    mfc_b200_params_t p{};
+    GridDesc g{};
+    int nf = 0, nd = 0, E = 0, b = 0;
+    bool viscous = false;
+    const Launchers *L = nullptr;
+    cudaStream_t st = nullptr;
+    double *state[3] = {nullptr, nullptr, nullptr};
+    int cur = 0;                       // which buffer holds q_cons_ts(1)
+    const double *last_q = nullptr;    // state of the most recent RHS evaluation (what q_prim_vf reflects)
+    double *prim = nullptr, *rhs = nullptr, *snap = nullptr;
+    double *coef[3] = {nullptr, nullptr, nullptr};
+    int clen[3] = {0, 0, 0}, coef_lo[3] = {0, 0, 0};
+    double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr};
+    std::vector<double> h_coef[3];
+    unsigned long long *stab_dev = nullptr, *stab_host = nullptr;
+    int bc[3][2];                      // effective codes: self-neighbours folded into periodic
+    double *sendbuf[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    double *recvbuf[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    int64_t launches = 0;
+    bool prof = false;
+    std::vector<ProfRec> prof_recs;
+    double prof_s[KC_COUNT] = {0};
+    int64_t prof_n[KC_COUNT] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+};
+Sim S;
+
+int fail(int code, const std::string &msg) { S.err = msg; return code; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? MFC_B200_ENOMEM : MFC_B200_ECUDA,        \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) return fail(MFC_B200_ENCCL, std::string(#call) + ": " + S.nccl.GetErrorString(r_)); \
+    } while (0)
+
+// launch bookkeeping: count, optional per-class CUDA-event timing on the launching stream
+struct Scope {
+    int kc; ProfRec r{};
+    explicit Scope(int kc_) : kc(kc_) {
+        if (S.prof) { r.kc = kc; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, S.st); }
+    }
+    void done(int n) {
+        S.launches += n;
+        if (S.prof) { cudaEventRecord(r.b, S.st); S.prof_recs.push_back(r); }
+    }
+};
+
+void prof_collect() {
+    if (S.prof_recs.empty()) return;
+    cudaStreamSynchronize(S.st);
+    for (auto &r : S.prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        S.prof_s[r.kc] += ms*1e-3; S.prof_n[r.kc] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    S.prof_recs.clear();
+}
+
+void free_all() {
+    auto fr = [](double *&p) { if (p) cudaFree(p); p = nullptr; };
+    for (auto &s : S.state) fr(s);
+    fr(S.prim); fr(S.rhs); fr(S.snap);
+    for (int d = 0; d < 3; d++) {
+        fr(S.coef[d]); fr(S.rds[d]); fr(S.ds[d]);
+        for (int s = 0; s < 2; s++) { fr(S.sendbuf[d][s]); fr(S.recvbuf[d][s]); }
+    }
+    if (S.stab_dev) { cudaFree(S.stab_dev); S.stab_dev = nullptr; }
+    if (S.stab_host) { cudaFreeHost(S.stab_host); S.stab_host = nullptr; }
+    if (S.ev0) { cudaEventDestroy(S.ev0); S.ev0 = nullptr; }
+    if (S.ev1) { cudaEventDestroy(S.ev1); S.ev1 = nullptr; }
+    if (S.comm && S.nccl.CommDestroy) { S.nccl.CommDestroy(S.comm); S.comm = nullptr; }
+    if (S.st) { cudaStreamDestroy(S.st); S.st = nullptr; }
+    for (auto &r : S.prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    S.prof_recs.clear();
+    S.inited = S.uploaded = false;
+}
+
+size_t field_bytes() { return (size_t)S.g.fstride*sizeof(double); }
+
+// ---- ghost cells: physical BCs (k_bc) and processor boundaries (pack / NCCL / unpack),
+// one direction after the other like m_rhs.fpp:686-908 ---------------------------------------
+int fill_ghosts(double *q) {
+    for (int d = 0; d < S.nd; d++) {
+        const bool phys = S.bc[d][0] < 0 || S.bc[d][1] < 0;
+        const bool proc = S.bc[d][0] >= 0 || S.bc[d][1] >= 0;
+        if (proc) {
+            if (!S.comm) return fail(MFC_B200_ESTATE, "processor boundary present but mfc_b200_comm_init was not called");
+            const long long n = slab_count(S.g, d)*S.E;
+            for (int s = 0; s < 2; s++) {
+                if (S.bc[d][s] < 0) continue;
+                HaloArgs h{S.g, q, S.sendbuf[d][s], d, s, S.E};
+                Scope sc(KC_PACK); sc.done(S.L->halo_pack(h, S.st));
+            }
+            // sends: [to beg: my first layers] [to end: my last layers];  receives in the
+            // opposite order so that two exchanges with the SAME peer (2 ranks, periodic)
+            // pair up correctly.
+            NK(S.nccl.GroupStart());
+            for (int s = 0; s < 2; s++)
+                if (S.bc[d][s] >= 0) NK(S.nccl.Send(S.sendbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, S.st));
+            for (int s = 1; s >= 0; s--)
+                if (S.bc[d][s] >= 0) NK(S.nccl.Recv(S.recvbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, S.st));
+            NK(S.nccl.GroupEnd());
+            for (int s = 0; s < 2; s++) {
+                if (S.bc[d][s] < 0) continue;
+                HaloArgs h{S.g, q, S.recvbuf[d][s], d, s, S.E};
+                Scope sc(KC_UNPACK); sc.done(S.L->halo_unpack(h, S.st));
+            }
+        }
+        if (phys) {
+            BcArgs a{S.g, q, d, S.E, S.nf + d, S.bc[d][0], S.bc[d][1]};
+            Scope sc(KC_BC); sc.done(S.L->bc(a, S.st));
+        }
+    }
+    return 0;
+}
+
+int run_prim(const double *q) {
+    PrimArgs a{};
+    a.g = S.g; a.q = q; a.prim = S.prim;
+    for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
+    Scope sc(KC_PRIM);
+    const int n = S.L->prim(S.nf, S.nd, a, S.st);
+    if (!n) return fail(MFC_B200_EUNSUPPORTED, "no kernel instantiated for this (num_fluids, num_dims)");
+    sc.done(n);
+    return 0;
+}
+
+int run_stability(const double *q, double dt, double stab[3]) {
+    StabArgs a{};
+    a.g = S.g; a.q = q; a.prim = S.prim; a.dt = dt; a.out = S.stab_dev;
+    for (int d = 0; d < 3; d++) a.ds[d] = S.ds[d];
+    for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
+    a.Re_size[0] = a.Re_size[1] = 0;
+    const double inf = INFINITY;
+    unsigned long long init[3] = {0ull, 0ull, 0ull};
+    std::memcpy(&init[2], &inf, sizeof(double));
+    std::memcpy(S.stab_host, init, sizeof(init));
+    CK(cudaMemcpyAsync(S.stab_dev, S.stab_host, sizeof(init), cudaMemcpyHostToDevice, S.st));
+    {
+        Scope sc(KC_STAB); sc.done(S.L->stability(S.nf, S.nd, a, S.st));
+    }
+    if (S.comm) {   // m_mpi_common.fpp:155-165: MAX / MIN over ranks (every rank gets the result)
+        NK(S.nccl.AllReduce(S.stab_dev, S.stab_dev, 2, ncclUint64, ncclMax, S.comm, S.st));
+        NK(S.nccl.AllReduce(S.stab_dev + 2, S.stab_dev + 2, 1, ncclUint64, ncclMin, S.comm, S.st));
+    }
+    CK(cudaMemcpyAsync(S.stab_host, S.stab_dev, sizeof(init), cudaMemcpyDeviceToHost, S.st));
+    CK(cudaStreamSynchronize(S.st));
+    if (stab) {
+        std::memcpy(&stab[0], &S.stab_host[0], sizeof(double));
+        if (S.viscous) { std::memcpy(&stab[1], &S.stab_host[1], sizeof(double)); std::memcpy(&stab[2], &S.stab_host[2], sizeof(double)); }
+    }
+    return 0;
+}
+
+// one s_compute_rhs on the stage state q (ghosts rebuilt in place), followed -- fused into the
+// last sweep -- by the RK statement rk_mode writes into qout
+int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt, int t_step,
+              bool first_stage, double stab[3]) {
+    int rc;
+    const bool stop = first_stage && t_step == S.p.t_step_stop;
+    // Reference quirk, kept: at t_step == t_step_stop s_compute_rhs returns (m_rhs.fpp:452)
+    // BEFORE it refreshes q_prim_vf (:659-675), so the last run_time.inf row is computed from
+    // the primitive variables of the previous RHS evaluation (m_time_steppers.fpp:288-290).
+    if (stop && S.p.run_time_info && stab && S.last_q)
+        if ((rc = run_stability(S.last_q, dt, stab))) return rc;
+    if ((rc = fill_ghosts(q))) return rc;                    // m_rhs.fpp:435
+    if ((rc = run_prim(q))) return rc;                       // :445-447
+    if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
+    S.last_q = q;
+    if (first_stage && S.p.run_time_info && stab)            // m_time_steppers.fpp:288-290
+        if ((rc = run_stability(q, dt, stab))) return rc;
+    for (int d = 0; d < S.nd; d++) {                         // :469
+        SweepArgs a{};
+        a.g = S.g; a.q = q; a.prim = S.prim; a.rhs = S.rhs; a.q1 = q1; a.qout = qout;
+        a.coef = S.coef[d]; a.clen = S.clen[d]; a.coef_lo = S.coef_lo[d]; a.rds = S.rds[d];
+        a.eps = S.p.weno_eps; a.dt = dt;
+        for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
+        a.bc_beg = S.p.bc[2*d]; a.bc_end = S.p.bc[2*d + 1];
+        a.first_dir = d == 0;
+        a.rk_mode = d == S.nd - 1 ? rk_mode : 0;
+        Scope sc(KC_SWEEP_X + d);
+        const int n = S.L->sweep(S.nf, S.nd, d, a, S.st);
+        if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
+        sc.done(n);
+    }
+    return 0;
+}
+
+int do_step(int t_step, double dt, double stab[3]) {
+    double *q1 = S.state[S.cur], *A = S.state[(S.cur + 1) % 3], *B = S.state[(S.cur + 2) % 3];
+    int rc;
+    const int ts = S.p.time_stepper;
+    if (ts == 1) {                                                         // m_time_steppers.fpp:129-193
+        if ((rc = rhs_stage(q1, 1, q1, A, dt, t_step, true, stab))) return rc;
+        if (t_step != S.p.t_step_stop) S.cur = (S.cur + 1) % 3;            // A becomes q_cons_ts(1)
+    } else if (ts == 2) {                                                  // :197-267
+        if ((rc = rhs_stage(q1, 1, q1, A, dt, t_step, true, stab))) return rc;
+        if (t_step == S.p.t_step_stop) return 0;
+        if ((rc = rhs_stage(A, 2, q1, q1, dt, t_step, false, nullptr))) return rc;
+    } else {                                                               // :271-362
+        if ((rc = rhs_stage(q1, 1, q1, A, dt, t_step, true, stab))) return rc;
+        if (t_step == S.p.t_step_stop) return 0;
+        if ((rc = rhs_stage(A, 3, q1, B, dt, t_step, false, nullptr))) return rc;
+        if ((rc = rhs_stage(B, 4, q1, q1, dt, t_step, false, nullptr))) return rc;
+    }
+    return 0;
+}
+
+// host field (Fortran sf(-b:m+b, ...), x fastest, contiguous) <-> padded device plane
+int copy_field(double *dev_plane, const double *host, bool to_device, cudaStream_t st) {
+    const GridDesc &g = S.g;
+    const size_t w = (size_t)(g.N[0] + 1 + 2*g.b)*sizeof(double);
+    double *d0 = dev_plane + (kXoff - g.b);
+    const size_t rows = (size_t)g.ey*g.ez;
+    if (to_device) CK(cudaMemcpy2DAsync(d0, (size_t)g.pitch*sizeof(double), host, w, w, rows, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemcpy2DAsync(const_cast<double *>(host), w, d0, (size_t)g.pitch*sizeof(double), w, rows, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mfc_b200_last_error(void) { return S.err.c_str(); }
+
+int mfc_b200_init(const mfc_b200_params_t *p) {
+    if (!p) return fail(MFC_B200_EINVAL, "params is NULL");
+    if (p->abi_version != MFC_B200_ABI_VERSION) return fail(MFC_B200_EINVAL, "ABI version mismatch");
+    if (S.inited) free_all();
+    // the checks of s_check_input_file that guard this path (m_start_up.fpp:147-229)
+    const int nd = p->num_dims, nf = p->num_fluids;
+    if (nd < 1 || nd > 3) return fail(MFC_B200_EINVAL, "Unsupported value of num_dims");
+    if (nf < 1 || nf > MFC_B200_MAX_FLUIDS) return fail(MFC_B200_EINVAL, "Unsupported value of num_fluids. Exiting ...");
+    if (p->sys_size != 2*nf + nd + 1) return fail(MFC_B200_EINVAL, "sys_size /= 2*num_fluids + num_dims + 1");
+    if (p->m <= 0) return fail(MFC_B200_EINVAL, "Unsupported value of m. Exiting ...");
+    if (p->n < 0 || (nd > 1) != (p->n > 0)) return fail(MFC_B200_EINVAL, "Unsupported value of n. Exiting ...");
+    if (p->p < 0 || (nd > 2) != (p->p > 0)) return fail(MFC_B200_EINVAL, "Unsupported value of p. Exiting ...");
+    if (p->weno_order != 1 && p->weno_order != 3 && p->weno_order != 5)
+        return fail(MFC_B200_EINVAL, "Unsupported value of weno_order. Exiting ...");
+    if (!(p->weno_eps > 0.0) || p->weno_eps > 1e-6) return fail(MFC_B200_EINVAL, "Unsupported value of weno_eps. Exiting ...");
+    if (p->time_stepper < 1 || p->time_stepper > 3) return fail(MFC_B200_EINVAL, "Unsupported value of time_stepper. Exiting ...");
+    bool visc = false;
+    for (int i = 0; i < nf; i++) {
+        if (!(p->gammas[i] > 0.0)) return fail(MFC_B200_EINVAL, "Unsupported value of fluid_pp(i)%gamma. Exiting ...");
+        if (p->pi_infs[i] < 0.0) return fail(MFC_B200_EINVAL, "Unsupported value of fluid_pp(i)%pi_inf. Exiting ...");
+        if (p->Re[i][0] > 0.0 || p->Re[i][1] > 0.0) visc = true;
+    }
+    const int polyn = (p->weno_order - 1)/2;
+    const int b_expect = visc ? 2*polyn + 2 : polyn + 2;
+    if (p->buff_size != b_expect) return fail(MFC_B200_EINVAL, "buff_size does not match weno_order / viscosity (m_global_parameters.fpp:356-360)");
+    for (int d = 0; d < nd; d++) {
+        if (!p->cb[d] || !p->ds[d] || !p->cc[d]) return fail(MFC_B200_EINVAL, "grid metric pointer is NULL");
+        for (int s = 0; s < 2; s++) {
+            const int c = p->bc[2*d + s];
+            if (c < -12 || c >= p->num_procs) return fail(MFC_B200_EINVAL, "Unsupported value of bc. Exiting ...");
+        }
+    }
+    if (p->weno_order != 5) return fail(MFC_B200_EUNSUPPORTED, "weno_order 1 and 3 are not built yet (SURVEY.md 8f-3)");
+    if (visc) return fail(MFC_B200_EUNSUPPORTED, "viscous fluxes are not built yet (SURVEY.md 8a-8)");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MFC_B200_ENODEVICE, "no CUDA device: libmfc_b200 has no CPU fallback");
+    int dev = p->device >= 0 ? p->device : p->proc_rank % ndev;      // p_main.fpp:95-99
+    if (dev >= ndev) return fail(MFC_B200_EINVAL, "device ordinal out of range");
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(MFC_B200_ENODEVICE, "kernels are built for sm_100a only");
+
+    S.p = *p;
+    for (int d = 0; d < 3; d++) S.p.cb[d] = S.p.cc[d] = S.p.ds[d] = nullptr;    // never keep host pointers
+    S.nf = nf; S.nd = nd; S.E = p->sys_size; S.b = p->buff_size; S.viscous = visc;
+    S.L = p->strict_math ? &launchers_strict() : &launchers_fast();
+    S.g = make_grid(p->m, p->n, p->p, nd, S.b);
+    for (int d = 0; d < 3; d++)
+        for (int s = 0; s < 2; s++) {
+            int c = p->bc[2*d + s];
+            if (c >= 0 && c == p->proc_rank) c = -1;     // my own periodic neighbour: plain periodic fill
+            S.bc[d][s] = d < nd ? c : -3;
+        }
+    CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&S.ev0)); CK(cudaEventCreate(&S.ev1));
+    const size_t sb = field_bytes()*S.E;
+    for (auto &s : S.state) { CK(cudaMalloc(&s, sb)); CK(cudaMemsetAsync(s, 0, sb, S.st)); }
+    CK(cudaMalloc(&S.prim, field_bytes()*(nd + 1))); CK(cudaMemsetAsync(S.prim, 0, field_bytes()*(nd + 1), S.st));
+    CK(cudaMalloc(&S.rhs, sb)); CK(cudaMemsetAsync(S.rhs, 0, sb, S.st));
+    CK(cudaMalloc(&S.stab_dev, 3*sizeof(unsigned long long)));
+    CK(cudaMallocHost(&S.stab_host, 3*sizeof(unsigned long long)));
+    for (int d = 0; d < nd; d++) {
+        const int N = S.g.N[d], b = S.b;
+        WenoTable t = build_weno5_table(p->cb[d], N, b);
+        S.clen[d] = t.len; S.coef_lo[d] = t.lo; S.h_coef[d] = t.data;
+        CK(cudaMalloc(&S.coef[d], t.data.size()*sizeof(double)));
+        CK(cudaMemcpyAsync(S.coef[d], S.h_coef[d].data(), t.data.size()*sizeof(double), cudaMemcpyHostToDevice, S.st));
+        std::vector<double> r((size_t)N + 1 + 2*b);
+        for (size_t i = 0; i < r.size(); i++) r[i] = 1.0/p->ds[d][i];          // "1d0/dx(k)" of m_rhs.fpp:571
+        CK(cudaMalloc(&S.rds[d], r.size()*sizeof(double)));
+        CK(cudaMalloc(&S.ds[d], r.size()*sizeof(double)));
+        CK(cudaMemcpy(S.rds[d], r.data(), r.size()*sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.ds[d], p->ds[d], r.size()*sizeof(double), cudaMemcpyHostToDevice));
+        for (int s = 0; s < 2; s++)
+            if (S.bc[d][s] >= 0) {
+                const size_t n = (size_t)slab_count(S.g, d)*S.E*sizeof(double);
+                CK(cudaMalloc(&S.sendbuf[d][s], n)); CK(cudaMalloc(&S.recvbuf[d][s], n));
+            }
+    }
+    CK(cudaStreamSynchronize(S.st));
+    S.cur = 0; S.launches = 0; S.inited = true; S.uploaded = false; S.last_q = nullptr;
+    S.err.clear();
+    return 0;
+}
+
+int mfc_b200_get_unique_id(unsigned char id[128]) {
+    if (!S.nccl.load(S.err)) return MFC_B200_ENCCL;
+    ncclUniqueId u;
+    NK(S.nccl.GetUniqueId(&u));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id, &u, 128);
+    return 0;
+}
+
+int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_comm_init before mfc_b200_init");
+    if (rank != S.p.proc_rank || nranks != S.p.num_procs) return fail(MFC_B200_EINVAL, "rank / nranks disagree with params");
+    if (!S.nccl.load(S.err)) return MFC_B200_ENCCL;
+    ncclUniqueId u;
+    std::memcpy(&u, id, 128);
+    NK(S.nccl.CommInitRank(&S.comm, nranks, u, rank));
+    return 0;
+}
+
+int mfc_b200_upload(const double *const q_cons[]) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_upload before mfc_b200_init");
+    for (int v = 0; v < S.E; v++) {
+        int rc = copy_field(S.state[S.cur] + (size_t)v*S.g.fstride, q_cons[v], true, S.st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(S.st));
+    S.uploaded = true;
+    return 0;
+}
+
+int mfc_b200_download(double *const q_cons[]) {
+    if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_download before mfc_b200_upload");
+    for (int v = 0; v < S.E; v++) {
+        int rc = copy_field(S.state[S.cur] + (size_t)v*S.g.fstride, q_cons[v], false, S.st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(S.st));
+    return 0;
+}
+
+int mfc_b200_download_prim(double *const q_prim[]) {
+    if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_download_prim before mfc_b200_upload");
+    // primitive variables of the most recent RHS evaluation's state (q_prim_qp): partial
+    // densities and volume fractions alias the conservative state (m_rhs.fpp:154-164)
+    int rc;
+    if ((rc = fill_ghosts(S.state[S.cur]))) return rc;
+    if ((rc = run_prim(S.state[S.cur]))) return rc;
+    for (int v = 0; v < S.E; v++) {
+        const bool is_prim = v >= S.nf && v <= S.nf + S.nd;
+        double *plane = is_prim ? S.prim + (size_t)(v - S.nf)*S.g.fstride : S.state[S.cur] + (size_t)v*S.g.fstride;
+        if ((rc = copy_field(plane, q_prim[v], false, S.st))) return rc;
+    }
+    CK(cudaStreamSynchronize(S.st));
+    return 0;
+}
+
+int mfc_b200_step(int t_step, double dt, double stab[3], double *step_seconds) {
+    if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step before mfc_b200_upload");
+    CK(cudaEventRecord(S.ev0, S.st));
+    double local[3] = {0, 0, 0};
+    int rc = do_step(t_step, dt, S.p.run_time_info ? (stab ? stab : local) : nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(S.ev1, S.st));
+    CK(cudaStreamSynchronize(S.st));
+    CK(cudaGetLastError());
+    if (step_seconds) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1)); *step_seconds = ms*1e-3; }
+    return 0;
+}
+
+int mfc_b200_step_async(int t_step, double dt, int n_steps) {
+    if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step_async before mfc_b200_upload");
+    for (int s = 0; s < n_steps; s++) {
+        int rc = do_step(t_step + s, dt, nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int mfc_b200_sync(void) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_sync before mfc_b200_init");
+    CK(cudaStreamSynchronize(S.st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mfc_b200_compute_rhs(const double *const q_cons[], double *const rhs[]) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_compute_rhs before mfc_b200_init");
+    double *scratch = S.state[(S.cur + 1) % 3];
+    int rc;
+    for (int v = 0; v < S.E; v++)
+        if ((rc = copy_field(scratch + (size_t)v*S.g.fstride, q_cons[v], true, S.st))) return rc;
+    if ((rc = rhs_stage(scratch, 0, scratch, scratch, 0.0, S.p.t_step_stop - 1, false, nullptr))) return rc;
+    const GridDesc &g = S.g;
+    const size_t w = (size_t)(g.N[0] + 1)*sizeof(double);
+    for (int v = 0; v < S.E; v++)
+        for (int l = 0; l <= g.N[2]; l++) {
+            const double *src = S.rhs + (size_t)v*g.fstride + g.at(0, 0, l);
+            double *dst = rhs[v] + (size_t)l*(g.N[0] + 1)*(g.N[1] + 1);
+            CK(cudaMemcpy2DAsync(dst, w, src, (size_t)g.pitch*sizeof(double), w, (size_t)g.N[1] + 1, cudaMemcpyDeviceToHost, S.st));
+        }
+    CK(cudaStreamSynchronize(S.st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mfc_b200_finalize(void) {
+    prof_collect();
+    free_all();
+    return 0;
+}
+
+int mfc_b200_get_weno_coefficients(int dir, double *poly_L, double *poly_R, double *d_L, double *d_R, double *beta) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_get_weno_coefficients before mfc_b200_init");
+    if (dir < 0 || dir >= S.nd) return fail(MFC_B200_EINVAL, "dir out of range");
+    const int n = S.clen[dir];
+    const double *c = S.h_coef[dir].data();
+    for (int i = 0; i < n; i++) {
+        for (int k = 0; k < 6; k++) {
+            if (poly_L) poly_L[(size_t)i*6 + k] = c[(size_t)k*n + i];
+            if (poly_R) poly_R[(size_t)i*6 + k] = c[(size_t)(6 + k)*n + i];
+        }
+        for (int k = 0; k < 3; k++) {
+            if (d_L) d_L[(size_t)i*3 + k] = c[(size_t)(12 + k)*n + i];
+            if (d_R) d_R[(size_t)i*3 + k] = c[(size_t)(15 + k)*n + i];
+        }
+        for (int k = 0; k < 9; k++)
+            if (beta) beta[(size_t)i*9 + k] = c[(size_t)(18 + k)*n + i];
+    }
+    return 0;
+}
+
+int64_t mfc_b200_kernel_launches(void) { return S.launches; }
+
+int mfc_b200_state_snapshot(void) {
+    if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_state_snapshot before mfc_b200_upload");
+    const size_t sb = field_bytes()*S.E;
+    if (!S.snap) CK(cudaMalloc(&S.snap, sb));
+    CK(cudaMemcpyAsync(S.snap, S.state[S.cur], sb, cudaMemcpyDeviceToDevice, S.st));
+    CK(cudaStreamSynchronize(S.st));
+    return 0;
+}
+
+int mfc_b200_state_restore(void) {
+    if (!S.snap) return fail(MFC_B200_ESTATE, "mfc_b200_state_restore without a snapshot");
+    CK(cudaMemcpyAsync(S.state[S.cur], S.snap, field_bytes()*S.E, cudaMemcpyDeviceToDevice, S.st));
+    CK(cudaStreamSynchronize(S.st));
+    return 0;
+}
+
+int mfc_b200_profile_enable(int on) {
+    prof_collect();
+    S.prof = on != 0;
+    if (on) for (int i = 0; i < KC_COUNT; i++) { S.prof_s[i] = 0; S.prof_n[i] = 0; }
+    return 0;
+}
+
+int mfc_b200_profile_get(int kc, double *seconds, int64_t *launches) {
+    if (kc < 0 || kc >= KC_COUNT) return fail(MFC_B200_EINVAL, "kernel class out of range");
+    prof_collect();
+    if (seconds) *seconds = S.prof_s[kc];
+    if (launches) *launches = S.prof_n[kc];
+    return 0;
+}
+
+const char *mfc_b200_kernel_name(int kc) { return kc >= 0 && kc < KC_COUNT ? kKernelNames[kc] : nullptr; }
+
+}  // extern "C"

@@ -147,7 +147,7 @@ class Oracle:
         return out
 
 
-def run_p_main(stepper, cfg: CaseConfig, n_steps: int | None = None):
+def run_p_main(stepper, cfg: CaseConfig):
     """The reference's time loop (src/simulation/p_main.fpp:196-318) around any object with a
     .step(t_step, dt) method -- shared by the oracle and (through Simulation) the CUDA path so
     both see the same dt sequence, including the end-of-run dt tweak (:287) and the
@@ -155,7 +155,7 @@ def run_p_main(stepper, cfg: CaseConfig, n_steps: int | None = None):
     t_step = cfg.t_step_start
     dt = cfg.dt
     mytime = 0.0 if t_step == 0 else t_step * dt
-    t_stop = cfg.t_step_stop if n_steps is None else cfg.t_step_start + n_steps
+    t_stop = cfg.t_step_stop
     finaltime = t_stop * dt
     rows = []
     while True:

