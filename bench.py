@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   (CPU restatement of the reference)
+
+One "step" is one SSP-RK3 time step (3 RHS evaluations: ghost fill, cons->prim, x/y/z WENO5 +
+HLLC sweeps with the update fused into the last sweep, plus the ICFL diagnostic) on the
+workload BASELINE.json's target names: the synthetic 3-D two-fluid shock-bubble at 512^3 cells
+PER GPU (configs[4]), weak-scaled over N GPUs with the reference's block decomposition and an
+NCCL halo exchange.  Other BASELINE configs: --workload advection_2d_1024 | shockbubble_2d_4096.
+
+Printed JSON (rank 0, one line):
+  value      Mcell-steps/s of the whole job, state resident in HBM, timed with CUDA events on
+             the library's launching stream, max over ranks
+  e2e        the same metric through the C ABI with HOST buffers: mfc_b200_upload of the state
+             from pinned host memory + K x mfc_b200_step (ICFL read back every step) +
+             mfc_b200_download, all inside the timed region
+  roofline   dominant kernel against the FP64-pipe roof (measured DFMA peak) -- this path is
+             FP64-bound once fused; roofline_hbm has the HBM view of the step
+  cpu_baseline  the CPU oracle (timing build, all host threads) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import dataclasses
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from microfc_b200 import cases, pre_process  # noqa: E402
+from microfc_b200.case import CaseConfig  # noqa: E402
+
+# measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.json); the
+# driver-written MEASURED_PEAKS.json has no FP64 entry
+FP64_PEAK_TFLOPS_FALLBACK = 34.07
+HBM_FALLBACK_GBS = 6650.0
+
+# algorithmic work per cell, SURVEY.md 8(d) / BASELINE.md 3 (source count of the reference)
+WENO_FLOPS = 84            # per variable per direction per cell, m_weno.fpp:476-531
+HLLC_FLOPS = {1: 170, 2: 206, 3: 250}   # per face, m_riemann_solvers.fpp:136-325
+DIV_FLOPS = 35             # flux divergence + source per direction, m_rhs.fpp:565-653
+PRIM_FLOPS = 22
+TOPOLOGY = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def sweep_flops_per_cell(E: int, nd: int, with_rk: bool) -> int:
+    return WENO_FLOPS * E + HLLC_FLOPS[nd] + DIV_FLOPS + (4 * E if with_rk else 0)
+
+
+def step_flops_per_cell(E: int, nd: int) -> int:
+    per_rhs = sum(sweep_flops_per_cell(E, nd, d == nd - 1) for d in range(nd)) + PRIM_FLOPS
+    return 3 * per_rhs
+
+
+def workload_case(name: str, n_gpus: int, cells: int | None):
+    px, py, pz = TOPOLOGY[n_gpus]
+    if name == "shockbubble_3d_512":
+        nc = cells or 512
+        d = cases.shockbubble_3d(ncx=nc * px, ncy=nc * py, ncz=nc * pz, Nt=10 ** 6)
+        desc = f"synthetic 3D two-fluid shock-bubble, {nc}^3 cells per GPU (BASELINE configs[4]; 3-D is an extension beyond the 1D/2D reference)"
+    elif name == "shockbubble_2d_4096":
+        nc = cells or 4096
+        d = cases.shockbubble_2d_cells(nc * px, nc * py, Nt=10 ** 6)
+        desc = f"examples/2D_shockbubble scaled to {nc}^2 cells per GPU (BASELINE configs[2])"
+    elif name == "advection_2d_1024":
+        nc = cells or 1024
+        d = cases.advection_2d(N=nc * px - 1, Nt=10 ** 6)
+        d['n'] = nc * py - 1
+        desc = f"examples/2D_advection at {nc}^2 cells per GPU (BASELINE configs[1])"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return cases.config(d), desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i] == "Active"})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def measured_peaks():
+    hbm, src = HBM_FALLBACK_GBS, "fallback"
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            hbm, src = float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    fp64, fsrc = FP64_PEAK_TFLOPS_FALLBACK, "measured (tools/fp64_peak.cu on this pool, profiles/r01_fp64_peak.json)"
+    return hbm, src, fp64, fsrc
+
+
+def cpu_reference_run(cfg_full: CaseConfig, steps: int, warmup: int, sample_cells: int):
+    """The CPU restatement of the reference (oracle timing build, OpenMP over all host threads)
+    on a bounded sample of the workload: same case, same step, fewer cells."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    nd = cfg_full.num_dims
+    if nd == 3:
+        d = cases.shockbubble_3d(nc=sample_cells, Nt=10 ** 6)
+        sample = f"{sample_cells}^3 cells of the same 3-D shock-bubble case"
+    else:
+        d = cases.shockbubble_2d_cells(sample_cells, sample_cells, Nt=10 ** 6) if cfg_full.bc[0][0] == -6 \
+            else cases.advection_2d(N=sample_cells - 1, Nt=10 ** 6)
+        sample = f"{sample_cells}^2 cells of the same 2-D case"
+    cfg = cases.config(d)
+    cb = pre_process.generate_grid(cfg)
+    q0 = pre_process.generate_initial_condition(cfg, cb)
+    o = oracle_lib.Oracle(cfg, cb, num_procs=1, kind="timing")
+    o.set_q(q0)
+    o.run_steps(0, warmup, cfg.dt)
+    secs = o.run_steps(warmup, steps, cfg.dt)
+    ncell = int(np.prod(cfg.shape_glb))
+    q = o.get_q()
+    assert np.isfinite(q).all()
+    return {"value": ncell * steps / secs / 1e6, "unit": "Mcell-steps/s", "cores": oracle_lib.load("timing").orc_num_threads(),
+            "kind": "port", "sample": f"{sample}, {steps} steps after {warmup} warm-up, all host threads (OpenMP); "
+            "the Fortran reference cannot be built in this image", "ms_per_step": secs / steps * 1e3,
+            "grind_ns_per_cell_eq_rhs": secs / steps / (ncell * cfg.sys_size * 3) * 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="shockbubble_3d_512")
+    ap.add_argument("--cells", type=int, default=None, help="cells per GPU and direction (default: the BASELINE size)")
+    ap.add_argument("--cpu-sample-cells", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus not in TOPOLOGY:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    K, W = args.steps, max(args.warmup, 0)
+    cfg, desc = workload_case(args.workload, args.gpus, args.cells)
+    nd, E = cfg.num_dims, cfg.sys_size
+    ncell_total = int(np.prod(cfg.shape_glb))
+    config = {"workload": desc, "cells_total": ncell_total, "cells_per_gpu": ncell_total // args.gpus,
+              "sys_size": E, "num_dims": nd, "time_stepper": "SSP-RK3", "weno_order": 5, "riemann_solver": "HLLC",
+              "run_time_info": bool(cfg.run_time_info), "decomposition": "x".join(map(str, TOPOLOGY[args.gpus])),
+              "l2": "state (>= 9 GB per GPU at the default size) is far larger than the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = args.cpu_sample_cells or (128 if nd == 3 else 1024)
+        r = cpu_reference_run(cfg, K, W, sample)
+        line = {"impl": "reference", "metric": "Mcell-steps/s", "value": r["value"], "unit": "Mcell-steps/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "grind_ns_per_cell_eq_rhs": r["grind_ns_per_cell_eq_rhs"],
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def bcast_id(mine):
+        obj = [mine]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+
+    from microfc_b200.simulation import Simulation
+    cb = pre_process.generate_grid(cfg)
+    sim = Simulation(cfg, cb, rank=rank, num_procs=world, device=local_rank, broadcast_id=bcast_id if world > 1 else None)
+    lay = sim.layout
+    # initial condition of this rank, generated in z-slabs straight into the (pinned) host
+    # buffer the Fortran host would own: sf(-b:m+b, -b:n+b, -b:p+b) per variable
+    host = torch.empty((E,) + sim.ghost_shape, dtype=torch.float64, pin_memory=True).numpy()
+    host[...] = 0.0
+    zs, ys, xs = lay.interior_slices()
+    b = sim.b
+    chunk = 32 if nd == 3 else (lay.N[1] + 1)
+    oz = b if nd > 2 else 0
+    oy = b if nd > 1 else 0
+    if nd == 3:
+        for z0 in range(zs.start, zs.stop, chunk):
+            z1 = min(z0 + chunk, zs.stop)
+            q = pre_process.generate_initial_condition(cfg, cb, box=(slice(z0, z1), ys, xs))
+            host[:, oz + z0 - zs.start:oz + z1 - zs.start, oy:oy + lay.N[1] + 1, b:b + lay.N[0] + 1] = q
+    else:
+        q = pre_process.generate_initial_condition(cfg, cb, box=(zs, ys, xs))
+        host[:, oz:oz + lay.N[2] + 1, oy:oy + lay.N[1] + 1, b:b + lay.N[0] + 1] = q
+    sim.upload_ghosted(host)
+    sim.snapshot()
+    dt = cfg.dt
+    state_bytes = host.nbytes
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    t_step = 0
+    for _ in range(W):
+        sim.step(t_step, dt); t_step += 1
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sim.profile(True)
+    launches0 = sim.kernel_launches()
+    barrier(); sim.sync()
+    sim.timer_start()
+    icfl = None
+    for _ in range(K):
+        icfl = sim.step(t_step, dt)[0]; t_step += 1
+    secs = sim.timer_stop()
+    barrier()
+    secs = max_over_ranks(secs)
+    launches = sim.kernel_launches() - launches0
+    prof = sim.profile_report()
+    sim.profile(False)
+    clocks = sampler.stop()
+    if not (icfl == icfl) or (cfg.run_time_info and icfl > 1.0):
+        raise SystemExit(f"unstable run: ICFL = {icfl}")
+    value = ncell_total * K / secs / 1e6
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        sim.restore()
+        barrier(); sim.sync()
+        t0 = time.perf_counter()
+        sim.upload_ghosted(host)                 # H2D from pinned host memory
+        ts = 0
+        for _ in range(K):
+            sim.step(ts, dt); ts += 1            # 24 B of stability data D2H every step
+        sim.download(out_ghosted=host)           # D2H into pinned host memory
+        sim.sync(); barrier()
+        e2e_secs = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": ncell_total * K / e2e_secs / 1e6, "unit": "Mcell-steps/s",
+               "h2d_bytes_per_step": state_bytes * world / K, "d2h_bytes_per_step": state_bytes * world / K + 24 * world,
+               "timed_region": f"mfc_b200_upload (pinned host -> HBM) + {K} x mfc_b200_step + mfc_b200_download, wall clock, max over ranks"}
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    hbm_peak, hbm_src, fp64_peak, fp64_src = measured_peaks()
+    sweeps = {k: v for k, v in prof.items() if k.startswith("k_sweep") and v[1] > 0}
+    dom = max(sweeps, key=lambda k: sweeps[k][0])
+    dom_t = sweeps[dom][0] / sweeps[dom][1]                      # average launch duration (CUDA events)
+    last_dir = {1: "k_sweep_x", 2: "k_sweep_march<y>", 3: "k_sweep_march<z>"}[nd]
+    cells_gpu = ncell_total // args.gpus
+    dom_flops = sweep_flops_per_cell(E, nd, dom == last_dir) * cells_gpu
+    roof = {"bound": "fp64", "kernel": dom, "achieved": dom_flops / dom_t / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": dom_flops / dom_t / 1e12 / fp64_peak, "traffic": None,
+            "avg_launch_ms": dom_t * 1e3, "algorithmic_flops_per_cell": sweep_flops_per_cell(E, nd, dom == last_dir),
+            "peak_source": fp64_src,
+            "note": "FP64-vector-pipe roof (no tensor cores on this path); algorithmic flops = source count of the reference "
+                    "(SURVEY.md 8d); see profiles/ for ncu pipe utilisation and DRAM traffic"}
+    step_bytes = 8 * E * 8 * cells_gpu
+    roof_hbm = {"bound": "hbm", "scope": "whole RK3 step", "achieved": step_bytes * K / secs / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": step_bytes * K / secs / 1e9 / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})",
+                "algorithmic_bytes_per_cell_step": 8 * E * 8}
+    kernel_share = {k: {"seconds": v[0], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample_cells or (128 if nd == 3 else 1024)
+        r = cpu_reference_run(cfg, 3, 1, sample)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "Mcell-steps/s", "value": value, "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "grind_ns_per_cell_eq_rhs": secs / K / (ncell_total * E * 3) * 1e9,
+                "gflops_algorithmic": step_flops_per_cell(E, nd) * ncell_total * K / secs / 1e9,
+                "e2e": e2e, "gpu_launches": launches * world, "clocks": clocks,
+                "roofline": roof, "roofline_hbm": roof_hbm, "kernel_time": kernel_share, "cpu_baseline": cpu,
+                "icfl_last": icfl}
+        print(json.dumps(line))
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

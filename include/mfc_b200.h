@@ -168,6 +168,12 @@ int64_t mfc_b200_kernel_launches(void);
 int mfc_b200_state_snapshot(void);
 int mfc_b200_state_restore(void);
 
+/* CUDA-event stopwatch on the library's own launching stream (torch.cuda.Event only sees
+   torch's current stream): _start records an event, _stop records another, synchronises and
+   returns the device time between them. */
+int mfc_b200_timer_start(void);
+int mfc_b200_timer_stop(double *seconds);
+
 /* Time of the dominant kernels accumulated with CUDA events on the launching stream
    since the last reset: out[0..n) seconds per kernel class, names via _kernel_name. */
 int mfc_b200_profile_enable(int on);

@@ -83,7 +83,7 @@ struct Sim {
     std::vector<ProfRec> prof_recs;
     double prof_s[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, sv0 = nullptr, sv1 = nullptr;
     std::string err;
 };
 Sim S;
@@ -139,6 +139,8 @@ void free_all() {
     if (S.stab_host) { cudaFreeHost(S.stab_host); S.stab_host = nullptr; }
     if (S.ev0) { cudaEventDestroy(S.ev0); S.ev0 = nullptr; }
     if (S.ev1) { cudaEventDestroy(S.ev1); S.ev1 = nullptr; }
+    if (S.sv0) { cudaEventDestroy(S.sv0); S.sv0 = nullptr; }
+    if (S.sv1) { cudaEventDestroy(S.sv1); S.sv1 = nullptr; }
     if (S.comm && S.nccl.CommDestroy) { S.nccl.CommDestroy(S.comm); S.comm = nullptr; }
     if (S.st) { cudaStreamDestroy(S.st); S.st = nullptr; }
     for (auto &r : S.prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -351,7 +353,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
             S.bc[d][s] = d < nd ? c : -3;
         }
     CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&S.ev0)); CK(cudaEventCreate(&S.ev1));
+    CK(cudaEventCreate(&S.ev0)); CK(cudaEventCreate(&S.ev1)); CK(cudaEventCreate(&S.sv0)); CK(cudaEventCreate(&S.sv1));
     const size_t sb = field_bytes()*S.E;
     for (auto &s : S.state) { CK(cudaMalloc(&s, sb)); CK(cudaMemsetAsync(s, 0, sb, S.st)); }
     CK(cudaMalloc(&S.prim, field_bytes()*(nd + 1))); CK(cudaMemsetAsync(S.prim, 0, field_bytes()*(nd + 1), S.st));
@@ -440,14 +442,14 @@ int mfc_b200_download_prim(double *const q_prim[]) {
 
 int mfc_b200_step(int t_step, double dt, double stab[3], double *step_seconds) {
     if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step before mfc_b200_upload");
-    CK(cudaEventRecord(S.ev0, S.st));
+    CK(cudaEventRecord(S.sv0, S.st));
     double local[3] = {0, 0, 0};
     int rc = do_step(t_step, dt, S.p.run_time_info ? (stab ? stab : local) : nullptr);
     if (rc) return rc;
-    CK(cudaEventRecord(S.ev1, S.st));
+    CK(cudaEventRecord(S.sv1, S.st));
     CK(cudaStreamSynchronize(S.st));
     CK(cudaGetLastError());
-    if (step_seconds) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1)); *step_seconds = ms*1e-3; }
+    if (step_seconds) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, S.sv0, S.sv1)); *step_seconds = ms*1e-3; }
     return 0;
 }
 
@@ -528,6 +530,23 @@ int mfc_b200_state_restore(void) {
     if (!S.snap) return fail(MFC_B200_ESTATE, "mfc_b200_state_restore without a snapshot");
     CK(cudaMemcpyAsync(S.state[S.cur], S.snap, field_bytes()*S.E, cudaMemcpyDeviceToDevice, S.st));
     CK(cudaStreamSynchronize(S.st));
+    return 0;
+}
+
+int mfc_b200_timer_start(void) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_timer_start before mfc_b200_init");
+    CK(cudaEventRecord(S.ev0, S.st));
+    return 0;
+}
+
+int mfc_b200_timer_stop(double *seconds) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_timer_stop before mfc_b200_init");
+    CK(cudaEventRecord(S.ev1, S.st));
+    CK(cudaEventSynchronize(S.ev1));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
+    if (seconds) *seconds = ms*1e-3;
     return 0;
 }
 

@@ -61,12 +61,16 @@ def _pre_process_centres(cb_glb: List[np.ndarray]) -> Tuple[List[np.ndarray], Li
     return cc, dmin
 
 
-def generate_initial_condition(cfg: CaseConfig, cb_glb: List[np.ndarray]) -> np.ndarray:
-    """Conservative variables on the global grid, shape (sys_size, Nz, Ny, Nx), C-order so
-    that x is fastest exactly like the Fortran arrays sf(0:m, 0:n[, 0:p])."""
+def generate_initial_condition(cfg: CaseConfig, cb_glb: List[np.ndarray], box=None) -> np.ndarray:
+    """Conservative variables, shape (sys_size, Nz, Ny, Nx), C-order so that x is fastest
+    exactly like the Fortran arrays sf(0:m, 0:n[, 0:p]).  ``box`` = (slice_z, slice_y, slice_x)
+    restricts the output to one rank's cells (pre_process runs decomposed too; the smoothing
+    length uses the GLOBAL minimum cell width, s_mpi_reduce_min m_start_up.fpp:720)."""
     nd, nf, E = cfg.num_dims, cfg.num_fluids, cfg.sys_size
     cc, dmin = _pre_process_centres(cb_glb)
-    Nz, Ny, Nx = cfg.shape_glb
+    if box is not None:
+        cc = [cc[d][box[2 - d]] for d in range(nd)]
+    Nx = len(cc[0]); Ny = len(cc[1]) if nd > 1 else 1; Nz = len(cc[2]) if nd > 2 else 1
     X = cc[0].reshape(1, 1, Nx)
     Y = cc[1].reshape(1, Ny, 1) if nd > 1 else np.zeros((1, 1, 1))
     Z = cc[2].reshape(Nz, 1, 1) if nd > 2 else np.zeros((1, 1, 1))

@@ -194,6 +194,14 @@ class Simulation:
     def restore(self) -> None:
         abi.check(self.L.mfc_b200_state_restore())
 
+    def timer_start(self) -> None:
+        abi.check(self.L.mfc_b200_timer_start())
+
+    def timer_stop(self) -> float:
+        s = C.c_double(0.0)
+        abi.check(self.L.mfc_b200_timer_stop(C.byref(s)))
+        return s.value
+
     def profile(self, on: bool) -> None:
         abi.check(self.L.mfc_b200_profile_enable(int(on)))
 
