@@ -23,6 +23,9 @@ struct SweepArgs {
     int rk_mode;           // 0: store RHS; 1..4: fused update, see rk_apply()
     int seg;               // cells per thread along the sweep (march kernels)
     int rows;              // rows per block (x kernel)
+    int variant;           // 2: TMA-ring kernels (k_xrow / k_march2), 1: v1 direct-load kernels
+    int coef_uniform;      // 1: cuni[] holds the coefficients of every cell of this direction
+    double cuni[kNumWenoCoef];   // uniform-grid WENO coefficients (COEF = 0 kernels)
 };
 
 struct BcArgs {

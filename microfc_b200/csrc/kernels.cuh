@@ -49,6 +49,34 @@ __device__ __forceinline__ double rk_apply(int mode, double q1, double qs, doubl
 }
 
 // ------------------------------------------------------------------------------------------
+// fast-build arithmetic helpers.  An IEEE-rounded FP64 division costs ~12.5 DFMA issue slots on
+// sm_100a (tools/fp64_peak.cu); the MUFU seed + two Newton steps below costs 4 and is accurate
+// to ~1 ulp (not correctly rounded) -- well inside the 1e-10 parity budget, re-gated by
+// tests/test_gpu_parity.py and the device self-test (mfc_b200_selftest_math).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// sqrt(n/d) for n, d > 0 as n*rsqrt(n*d): one MUFU seed, two Newton steps, no division
+__device__ __forceinline__ double sqrt_ratio_fast(double n, double d) {
+    const double x = n*d;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 5e-1*x;
+    double e = fma(-(h*y), y, 5e-1);
+    y = fma(y, e, y);
+    e = fma(-(h*y), y, 5e-1);
+    y = fma(y, e, y);
+    return n*y;
+}
+
+// ------------------------------------------------------------------------------------------
 // WENO5-JS on one 5-cell stencil v[0..4] = v(j-2..j+2), m_weno.fpp:476-531.
 // c[] = the 27 grid-dependent coefficients of cell j:
 //   c[0..5]  poly_coef_cbL(j,k,q) k-major    c[6..11] poly_coef_cbR
@@ -95,7 +123,7 @@ __device__ __forceinline__ void weno5(const double v[5], const double c[27], dou
     const double DL = aL0 + aL1 + aL2, DR = aR0 + aR1 + aR2;
     const double NL = fma(aL0, pl0, fma(aL1, pl1, aL2*pl2));
     const double NR = fma(aR0, pr0, fma(aR1, pr1, aR2*pr2));
-    const double inv = 1.0/(DL*DR);
+    const double inv = rcp_fast(DL*DR);
     vL = NL*(DR*inv);
     vR = NR*(DL*inv);
 #endif
@@ -112,6 +140,61 @@ template <int NF, int ND, int NRM>
 __device__ __forceinline__ void hllc(const double *L, const double *R, const double *gam, const double *pinf,
                                      double *F, double &uf) {
     constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+#if !MFC_STRICT
+    // Fast build: the same solver with three exact-arithmetic identities applied.
+    //  (1) H - v^2/2 = ((Gamma+1) p + Pi)/rho, so c = sqrt(((Gamma+1) p + Pi)/(rho Gamma)) without
+    //      forming E or H (2 divisions + the cancellation H - v^2/2 saved per side).
+    //  (2) xi_M, xi_P are the 0/1 indicators of the sign of s_S (:254-255): only the upwind
+    //      star state contributes, so only that side is evaluated (selects, no branch).
+    //  (3) 1/(s_K - s_S) and 1/(s_K - u_K) share one reciprocal of their product.
+    double v2L = 0.0, v2R = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        v2L = fma(L[MOM + i], L[MOM + i], v2L);
+        v2R = fma(R[MOM + i], R[MOM + i], v2R);
+    }
+    double rho_L = 0.0, gamma_L = 0.0, pi_inf_L = 0.0, rho_R = 0.0, gamma_R = 0.0, pi_inf_R = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        rho_L = rho_L + L[i];
+        gamma_L = fma(L[ADV + i], gam[i], gamma_L);
+        pi_inf_L = fma(L[ADV + i], pinf[i], pi_inf_L);
+        rho_R = rho_R + R[i];
+        gamma_R = fma(R[ADV + i], gam[i], gamma_R);
+        pi_inf_R = fma(R[ADV + i], pinf[i], pi_inf_R);
+    }
+    const double pres_L = L[EN], pres_R = R[EN];
+    const double uL = L[MOM + NRM], uR = R[MOM + NRM];
+    const double c_L = sqrt_ratio_fast(fma(gamma_L + 1.0, pres_L, pi_inf_L), rho_L*gamma_L);
+    const double c_R = sqrt_ratio_fast(fma(gamma_R + 1.0, pres_R, pi_inf_R), rho_R*gamma_R);
+    const double s_L = fmin(uL - c_L, uR - c_R);
+    const double s_R = fmax(uR + c_R, uL + c_L);
+    const double mL = rho_L*(s_L - uL), mR = rho_R*(s_R - uR);
+    const double s_S = (pres_R - pres_L + mL*uL - mR*uR)*rcp_fast(mL - mR);
+    const bool left = !signbit(s_S);                     // xi_M = 1 (:254)
+    const double rho = left ? rho_L : rho_R, u = left ? uL : uR, pres = left ? pres_L : pres_R;
+    const double s_K = left ? s_L : s_R;
+    const double s_MP = left ? fmin(0.0, s_L) : fmax(0.0, s_R);
+    const double E_K = fma(left ? gamma_L : gamma_R, pres, left ? pi_inf_L : pi_inf_R) + 5e-1*rho*(left ? v2L : v2R);
+    const double da = s_K - s_S, db = s_K - u;
+    const double rab = rcp_fast(da*db);
+    const double xi = db*db*rab;                         // (s_K - u_K)/(s_K - s_S)
+    const double p_over = pres*da*rab;                   // p_K/(s_K - u_K)
+    const double w = fma(s_MP, xi - 1.0, u);             // u_K + s_MP (xi_K - 1)
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        F[i] = (left ? L[i] : R[i])*w;
+        F[ADV + i] = (left ? L[ADV + i] : R[ADV + i])*w;
+    }
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        const double vi = left ? L[MOM + i] : R[MOM + i];
+        if (i == NRM) F[MOM + i] = fma(rho, fma(u, u, s_MP*fma(xi, s_S, -u)), pres);
+        else F[MOM + i] = rho*vi*w;
+    }
+    F[EN] = fma(u, E_K + pres, s_MP*(fma(xi, fma(s_S - u, fma(rho, s_S, p_over), E_K), -E_K)));
+    uf = w;
+#else
     double vel_L_rms = 0.0, vel_R_rms = 0.0;                            // :138-145
 #pragma unroll
     for (int i = 0; i < ND; i++) {
@@ -165,6 +248,7 @@ __device__ __forceinline__ void hllc(const double *L, const double *R, const dou
     for (int i = 0; i < NF; i++)                                        // :304-310
         F[ADV + i] = xi_M*L[ADV + i]*(uL + s_M*(xi_L - 1.0)) + xi_P*R[ADV + i]*(uR + s_P*(xi_R - 1.0));
     uf = xi_M*(uL + s_M*(xi_L - 1.0)) + xi_P*(uR + s_P*(xi_R - 1.0));   // :316-325
+#endif
 }
 
 // pointer to reconstruction variable v of the stage state: partial densities and volume
@@ -324,6 +408,322 @@ __global__ void __launch_bounds__(128) k_sweep_march(const __grid_constant__ Swe
         }
 #pragma unroll
         for (int v = 0; v < E; v++) vRp[v] = vR[v];
+    }
+}
+
+// ==========================================================================================
+// v2 sweep kernels: the stage state streams HBM -> shared memory through the TMA engine
+// (cp.async.bulk, SASS UBLKCP) into a ring of row slots guarded by mbarriers; every value is
+// fetched from HBM exactly once per sweep, the conservative -> primitive conversion
+// (m_variables_conversion.fpp:326-373) happens in place in the ring (no q_prim planes in HBM,
+// no k_prim launch on the hot path), and the 5-point stencils are read with conflict-free
+// LDS.64.  COEF = 0: uniform grid, the 27 WENO coefficients are kernel-parameter constants
+// (constant-bank operands of the DFMAs); COEF = 1: per-cell coefficient tables.
+// ==========================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "MFC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra MFC_DONE;\n"
+        "bra MFC_WAIT;\n"
+        "MFC_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// generic-proxy accesses to a slot must be ordered before the async proxy overwrites it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kTX = 128;       // doubles per staged row segment (1 KB)
+constexpr int kRingY = 8;      // row slots of the y/z march ring: 5 live rows + 3 in flight
+constexpr int kRingX = 4;      // row slots of the x kernel: 1 live row + 3 in flight
+constexpr int kWarpCells = 30; // cells finished per warp and row in the x kernel
+
+// cons -> prim of one cell held in a ring slot (stride kTX between variables), in place:
+// momenta become velocities, the energy becomes the pressure (:187-227, :353-362, :98-106)
+template <int NF, int ND>
+__device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, const double *pinf) {
+    constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+    double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        const double al = cellp[(ADV + i)*kTX];
+        rho = rho + cellp[i*kTX];
+        gamma = gamma + al*gam[i];
+        pi_inf = pi_inf + al*pinf[i];
+    }
+    rho = fmax(rho, 1e-16);
+    double dyn = 0.0;
+#if MFC_STRICT
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        const double mom = cellp[(MOM + i)*kTX];
+        const double u = mom/rho;
+        cellp[(MOM + i)*kTX] = u;
+        dyn = dyn + 5e-1*mom*u;
+    }
+    cellp[EN*kTX] = (cellp[EN*kTX] - dyn - pi_inf)/gamma;
+#else
+    const double ir = rcp_fast(rho), ig = rcp_fast(gamma);
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        const double mom = cellp[(MOM + i)*kTX];
+        const double u = mom*ir;
+        cellp[(MOM + i)*kTX] = u;
+        dyn = fma(5e-1*mom, u, dyn);
+    }
+    cellp[EN*kTX] = (cellp[EN*kTX] - dyn - pi_inf)*ig;
+#endif
+}
+
+template <int COEF>
+__device__ __forceinline__ void get_coef(const SweepArgs &a, int cell, double c[27]) {
+    if (COEF == 0) {
+#pragma unroll
+        for (int i = 0; i < 27; i++) c[i] = a.cuni[i];
+    } else {
+        load_coef(a, cell, c);
+    }
+}
+
+// RHS of one cell + fused RK stage; al[] = the cell's volume fractions of the stage state
+// (taken from the ring), every other operand streams from / to HBM.
+template <int NF, int ND>
+__device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell, double rds, const double *al,
+                                             const double *Fm, double ufm, const double *Fp, double ufp) {
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1;
+    const long long fs = a.g.fstride;
+    double r[E];
+#pragma unroll
+    for (int v = 0; v < E; v++) r[v] = a.first_dir ? 0.0 : a.rhs[v*fs + cell];
+    double q1[E], qs[E];
+    if (a.rk_mode != 0) {
+#pragma unroll
+        for (int v = 0; v < E; v++) q1[v] = a.q1[v*fs + cell];
+    }
+    if (a.rk_mode >= 2) {
+#pragma unroll
+        for (int v = 0; v < E; v++) qs[v] = v >= ADV ? al[v - ADV] : a.q[v*fs + cell];
+    }
+#pragma unroll
+    for (int v = 0; v < E; v++) {
+        double x = rds*(Fm[v] - Fp[v]);
+        if (!a.first_dir) x = r[v] + x;
+        if (v >= ADV) x = x + rds*al[v - ADV]*(ufp - ufm);
+        if (a.rk_mode == 0) a.rhs[v*fs + cell] = x;
+        else a.qout[v*fs + cell] = rk_apply(a.rk_mode, q1[v], a.rk_mode >= 2 ? qs[v] : 0.0, x, a.dt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x sweep, v2.  A CTA of 4 warps owns 120 consecutive cells of a row and streams `rows`
+// consecutive rows through a 4-slot ring (one bulk copy of 128 doubles per variable and row,
+// issued by one thread, three rows ahead of the compute).  Within a row the work is the warp
+// shuffle pencil of v1: lane = cell, neighbours' face states / fluxes by shuffle.
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND, int COEF>
+__global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = E*kTX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ring + R*SLOT);
+    const GridDesc &g = a.g;
+    const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
+    const int j0 = blockIdx.x*(4*kWarpCells);          // first cell finished by this CTA
+    const int k0 = blockIdx.y*a.rows, l = blockIdx.z;
+    const int nrows = min(a.rows, g.N[1] + 1 - k0);
+    const int x0 = j0 - 4;                             // first staged column
+    const int nx = min(kTX, g.pitch - (x0 + kXoff));   // staged doubles per row (even)
+    const unsigned row_bytes = (unsigned)nx*8u;
+    const long long fs = g.fstride;
+    const long long base = g.at(x0, k0, l);
+    if (tx == 0) {
+        for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int r) {
+        const int slot = r & (R - 1);
+        mbar_expect_tx(&bar[slot], row_bytes*E);
+#pragma unroll
+        for (int v = 0; v < E; v++)
+            bulk_g2s(ring + slot*SLOT + v*kTX, a.q + v*fs + base + (long long)r*g.sy, row_bytes, &bar[slot]);
+    };
+    if (tx == 0)
+        for (int r = 0; r < min(R, nrows); r++) issue(r);
+
+    const int jw = j0 + warp*kWarpCells;               // first cell finished by this warp
+    const bool warp_on = jw <= g.N[0];
+    const int j_raw = jw - 1 + lane;
+    const int j = min(j_raw, g.N[0] + 1);              // clamped lanes never store
+    const int sx = j - x0;                             // staged index of my cell (3 .. 124)
+    double c[27];
+    get_coef<COEF>(a, j, c);
+    const double rds = a.rds[j + g.b];
+    const unsigned full = 0xffffffffu;
+    const bool conv_on = tx < nx;
+
+    for (int r = 0; r < nrows; r++) {
+        const int slot = r & (R - 1);
+        double *row = ring + slot*SLOT;
+        mbar_wait(&bar[slot], (unsigned)(r/R) & 1u);
+        if (conv_on) prim_in_place<NF, ND>(row + tx, a.gammas, a.pi_infs);
+        fence_proxy_async();
+        __syncthreads();                               // row converted; everyone is done with row r-1
+        if (tx == 0 && r >= 1 && r - 1 + R < nrows) issue(r - 1 + R);
+        if (!warp_on) continue;
+        const double *p = row + sx;
+        double vL[E], vR[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            double s[5];
+#pragma unroll
+            for (int t = 0; t < 5; t++) s[t] = p[v*kTX + (t - 2)];
+            weno5(s, c, a.eps, vL[v], vR[v]);
+        }
+        double Ls[E], Rs[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            Ls[v] = vR[v];
+            Rs[v] = __shfl_down_sync(full, vL[v], 1);
+        }
+        if (a.bc_beg == -4 && j_raw == -1) {           // m_riemann_solvers.fpp:480-487
+#pragma unroll
+            for (int v = 0; v < E; v++) Ls[v] = Rs[v];
+        }
+        if (a.bc_end == -4 && j_raw == g.N[0]) {       // :515-523
+#pragma unroll
+            for (int v = 0; v < E; v++) Rs[v] = Ls[v];
+        }
+        double F[E], uf;
+        hllc<NF, ND, 0>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+        double Fm[E], ufm;
+#pragma unroll
+        for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
+        ufm = __shfl_up_sync(full, uf, 1);
+        if (lane >= 1 && lane <= kWarpCells && j_raw <= g.N[0]) {
+            double al[NF];
+#pragma unroll
+            for (int i = 0; i < NF; i++) al[i] = p[(ADV + i)*kTX];
+            finish_cell2<NF, ND>(a, g.at(j, k0 + r, l), rds, al, Fm, ufm, F, uf);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// y / z sweep, v2.  A CTA owns 128 consecutive x columns at one transverse index and marches
+// a pencil segment s0..s1 along the sweep direction.  Rows s0-3 .. s1+3 stream through an
+// 8-slot ring (5 live rows of the stencil + 3 rows in flight); every thread converts, reads
+// and reconstructs only its own column, carrying the previous cell's right-face state and the
+// previous face's flux in registers as in v1, so the only block-wide synchronisation is the
+// slot hand-back once per row.
+// ------------------------------------------------------------------------------------------
+template <int NF, int ND, int DIR, int COEF>
+__global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingY, SLOT = E*kTX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ring + R*SLOT);
+    const GridDesc &g = a.g;
+    const int tx = threadIdx.x;
+    const int j0 = blockIdx.x*kTX, j = j0 + tx;
+    const int t = blockIdx.z;
+    const int s0 = blockIdx.y*a.seg;
+    const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
+    const bool on = j <= g.N[0];
+    const long long ss = DIR == 1 ? g.sy : g.sz;
+    const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the tile
+    const int nx = min(kTX, g.pitch - (j0 + kXoff));
+    const unsigned row_bytes = (unsigned)nx*8u;
+    const long long fs = g.fstride;
+    const int r_first = s0 - 3, r_last = s1 + 3;
+    if (tx == 0) {
+        for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int r) {
+        const int slot = (r - r_first) & (R - 1);
+        mbar_expect_tx(&bar[slot], row_bytes*E);
+#pragma unroll
+        for (int v = 0; v < E; v++)
+            bulk_g2s(ring + slot*SLOT + v*kTX, a.q + v*fs + base + (long long)r*ss, row_bytes, &bar[slot]);
+    };
+    int next_issue = r_first + R;                      // only thread 0 issues, everyone counts
+    if (tx == 0)
+        for (int r = r_first; r < r_first + R && r <= r_last; r++) issue(r);
+
+    int conv = r_first;                                // next row to wait for and convert
+    double vRp[E], Fp[E], ufp = 0.0;
+#pragma unroll
+    for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
+    const long long col = base + tx;
+    for (int s = s0 - 1; s <= s1 + 1; s++) {
+        while (conv <= s + 2) {
+            const int i = conv - r_first, slot = i & (R - 1);
+            mbar_wait(&bar[slot], (unsigned)(i/R) & 1u);
+            if (on) prim_in_place<NF, ND>(ring + slot*SLOT + tx, a.gammas, a.pi_infs);
+            conv++;
+        }
+        if (on) {
+            double c[27];
+            get_coef<COEF>(a, s, c);
+            const double *p[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) p[q] = ring + ((s - 2 + q - r_first) & (R - 1))*SLOT + tx;
+            double vL[E], vR[E];
+#pragma unroll
+            for (int v = 0; v < E; v++) {
+                double st[5];
+#pragma unroll
+                for (int q = 0; q < 5; q++) st[q] = p[q][v*kTX];
+                weno5(st, c, a.eps, vL[v], vR[v]);
+            }
+            if (s >= s0) {
+                double Ls[E], Rs[E];
+#pragma unroll
+                for (int v = 0; v < E; v++) { Ls[v] = vRp[v]; Rs[v] = vL[v]; }
+                if (a.bc_beg == -4 && s == 0) {
+#pragma unroll
+                    for (int v = 0; v < E; v++) Ls[v] = Rs[v];
+                }
+                if (a.bc_end == -4 && s == g.N[DIR] + 1) {
+#pragma unroll
+                    for (int v = 0; v < E; v++) Rs[v] = Ls[v];
+                }
+                double F[E], uf;
+                hllc<NF, ND, DIR>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+                if (s >= s0 + 1) {
+                    double al[NF];
+#pragma unroll
+                    for (int i = 0; i < NF; i++) al[i] = p[1][(ADV + i)*kTX];      // row s-1
+                    finish_cell2<NF, ND>(a, col + (long long)(s - 1)*ss, a.rds[s - 1 + g.b], al, Fp, ufp, F, uf);
+                }
+#pragma unroll
+                for (int v = 0; v < E; v++) Fp[v] = F[v];
+                ufp = uf;
+            }
+#pragma unroll
+            for (int v = 0; v < E; v++) vRp[v] = vR[v];
+        }
+        fence_proxy_async();
+        __syncthreads();                               // row s-2 is dead for the whole CTA
+        if (next_issue <= r_last) {
+            if (tx == 0) issue(next_issue);
+            next_issue++;
+        }
     }
 }
 

@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,6 +71,9 @@ struct Sim {
     double *prim = nullptr, *rhs = nullptr, *snap = nullptr;
     double *coef[3] = {nullptr, nullptr, nullptr};
     int clen[3] = {0, 0, 0}, coef_lo[3] = {0, 0, 0};
+    int coef_uniform[3] = {0, 0, 0};   // every cell of the direction has the same 27 coefficients (to 1e-12)
+    double cuni[3][kNumWenoCoef];
+    int variant = 2;                   // sweep kernel generation (MFC_B200_KERNELS=1 selects the v1 kernels)
     double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr};
     std::vector<double> h_coef[3];
     unsigned long long *stab_dev = nullptr, *stab_host = nullptr;
@@ -199,6 +203,8 @@ int run_prim(const double *q) {
 }
 
 int run_stability(const double *q, double dt, double stab[3]) {
+    // the v2 sweeps convert in shared memory; q_prim_vf is materialised only for this diagnostic
+    if (S.variant == 2) { int rc = run_prim(q); if (rc) return rc; }
     StabArgs a{};
     a.g = S.g; a.q = q; a.prim = S.prim; a.dt = dt; a.out = S.stab_dev;
     for (int d = 0; d < 3; d++) a.ds[d] = S.ds[d];
@@ -237,7 +243,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     if (stop && S.p.run_time_info && stab && S.last_q)
         if ((rc = run_stability(S.last_q, dt, stab))) return rc;
     if ((rc = fill_ghosts(q))) return rc;                    // m_rhs.fpp:435
-    if ((rc = run_prim(q))) return rc;                       // :445-447
+    if (S.variant != 2 && (rc = run_prim(q))) return rc;     // :445-447 (v2: fused into the sweeps)
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
     S.last_q = q;
     if (first_stage && S.p.run_time_info && stab)            // m_time_steppers.fpp:288-290
@@ -251,6 +257,8 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.bc_beg = S.p.bc[2*d]; a.bc_end = S.p.bc[2*d + 1];
         a.first_dir = d == 0;
         a.rk_mode = d == S.nd - 1 ? rk_mode : 0;
+        a.variant = S.variant; a.coef_uniform = S.coef_uniform[d];
+        for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
         Scope sc(KC_SWEEP_X + d);
         const int n = S.L->sweep(S.nf, S.nd, d, a, S.st);
         if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
@@ -345,6 +353,10 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     for (int d = 0; d < 3; d++) S.p.cb[d] = S.p.cc[d] = S.p.ds[d] = nullptr;    // never keep host pointers
     S.nf = nf; S.nd = nd; S.E = p->sys_size; S.b = p->buff_size; S.viscous = visc;
     S.L = p->strict_math ? &launchers_strict() : &launchers_fast();
+    {
+        const char *e = std::getenv("MFC_B200_KERNELS");
+        S.variant = (e && e[0] == '1') ? 1 : 2;
+    }
     S.g = make_grid(p->m, p->n, p->p, nd, S.b);
     for (int d = 0; d < 3; d++)
         for (int s = 0; s < 2; s++) {
@@ -364,6 +376,18 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         const int N = S.g.N[d], b = S.b;
         WenoTable t = build_weno5_table(p->cb[d], N, b);
         S.clen[d] = t.len; S.coef_lo[d] = t.lo; S.h_coef[d] = t.data;
+        {   // uniform grid?  then the per-cell coefficients agree to rounding and the fast
+            // kernels take them (those of the middle cell) as constants
+            const int mid = t.len/2;
+            bool uni = true;
+            for (int c = 0; c < kNumWenoCoef; c++) {
+                const double ref = t.data[(size_t)c*t.len + mid];
+                S.cuni[d][c] = ref;
+                for (int i = 0; i < t.len && uni; i++)
+                    if (std::fabs(t.data[(size_t)c*t.len + i] - ref) > 1e-12*std::fabs(ref) + 1e-300) uni = false;
+            }
+            S.coef_uniform[d] = uni ? 1 : 0;
+        }
         CK(cudaMalloc(&S.coef[d], t.data.size()*sizeof(double)));
         CK(cudaMemcpyAsync(S.coef[d], S.h_coef[d].data(), t.data.size()*sizeof(double), cudaMemcpyHostToDevice, S.st));
         std::vector<double> r((size_t)N + 1 + 2*b);
