@@ -23,6 +23,10 @@ struct SweepArgs {
     int rk_mode;           // 0: store RHS; 1..4: fused update, see rk_apply()
     int seg;               // cells per thread along the sweep (march kernels)
     int rows;              // rows per block (x kernel)
+    // fused stability criterion (x kernel of stage 1, inviscid fast build): ICFL max of the
+    // cells this kernel finishes, m_data_output.fpp:215-233; nullptr = off
+    unsigned long long *stab_out;
+    const double *rds_t[2];      // 1/ds of the two transverse directions (y, z)
     int variant;           // 2: TMA-ring kernels (k_xrow / k_march2), 1: v1 direct-load kernels
     int coef_uniform;      // 1: cuni[] holds the coefficients of every cell of this direction
     double cuni[kNumWenoCoef];   // uniform-grid WENO coefficients (COEF = 0 kernels)

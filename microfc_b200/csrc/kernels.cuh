@@ -446,21 +446,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
 // generic-proxy accesses to a slot must be ordered before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kTX = 128;       // doubles per staged row segment (1 KB)
+constexpr int kWX = 40;        // doubles staged per warp, row and variable by the x kernel (36 used)
+constexpr int kWY = 32;        // columns per warp in the y/z march
 constexpr int kRingY = 8;      // row slots of the y/z march ring: 5 live rows + 3 in flight
 constexpr int kRingX = 4;      // row slots of the x kernel: 1 live row + 3 in flight
 constexpr int kWarpCells = 30; // cells finished per warp and row in the x kernel
+constexpr int kWarpsPerCta = 4;
 
-// cons -> prim of one cell held in a ring slot (stride kTX between variables), in place:
+// cons -> prim of one cell held in a ring slot (stride LD between variables), in place:
 // momenta become velocities, the energy becomes the pressure (:187-227, :353-362, :98-106)
-template <int NF, int ND>
+template <int NF, int ND, int LD>
 __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, const double *pinf) {
     constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
     double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
 #pragma unroll
     for (int i = 0; i < NF; i++) {
-        const double al = cellp[(ADV + i)*kTX];
-        rho = rho + cellp[i*kTX];
+        const double al = cellp[(ADV + i)*LD];
+        rho = rho + cellp[i*LD];
         gamma = gamma + al*gam[i];
         pi_inf = pi_inf + al*pinf[i];
     }
@@ -469,22 +471,22 @@ __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, 
 #if MFC_STRICT
 #pragma unroll
     for (int i = 0; i < ND; i++) {
-        const double mom = cellp[(MOM + i)*kTX];
+        const double mom = cellp[(MOM + i)*LD];
         const double u = mom/rho;
-        cellp[(MOM + i)*kTX] = u;
+        cellp[(MOM + i)*LD] = u;
         dyn = dyn + 5e-1*mom*u;
     }
-    cellp[EN*kTX] = (cellp[EN*kTX] - dyn - pi_inf)/gamma;
+    cellp[EN*LD] = (cellp[EN*LD] - dyn - pi_inf)/gamma;
 #else
     const double ir = rcp_fast(rho), ig = rcp_fast(gamma);
 #pragma unroll
     for (int i = 0; i < ND; i++) {
-        const double mom = cellp[(MOM + i)*kTX];
+        const double mom = cellp[(MOM + i)*LD];
         const double u = mom*ir;
-        cellp[(MOM + i)*kTX] = u;
+        cellp[(MOM + i)*LD] = u;
         dyn = fma(5e-1*mom, u, dyn);
     }
-    cellp[EN*kTX] = (cellp[EN*kTX] - dyn - pi_inf)*ig;
+    cellp[EN*LD] = (cellp[EN*LD] - dyn - pi_inf)*ig;
 #endif
 }
 
@@ -498,219 +500,351 @@ __device__ __forceinline__ void get_coef(const SweepArgs &a, int cell, double c[
     }
 }
 
-// RHS of one cell + fused RK stage; al[] = the cell's volume fractions of the stage state
-// (taken from the ring), every other operand streams from / to HBM.
-template <int NF, int ND>
-__device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell, double rds, const double *al,
-                                             const double *Fm, double ufm, const double *Fp, double ufp) {
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// operands of finish_cell2 that stream from HBM, fetched ahead of the Riemann solve.
+// ACC: the RHS of earlier directions is accumulated (m_rhs.fpp:610-620); RK: this is the last
+// direction, the TVD-RK statement a.rk_mode (1..4, or 0 = store the RHS) is fused in.
+//
+// Strict build: q_cons_ts(1) and the stage state are read back from HBM for the update.
+// Fast build: the stage state's momenta and energy are rebuilt from the primitive variables
+// held in the ring (mom = rho u, E = Gamma p + Pi + rho |u|^2/2; 1-ulp round trip), so stage 1
+// (q1 == stage state) reads nothing and stages 2/3 read only q_cons_ts(1).
+template <int E, bool ACC, bool RK>
+struct CellIn {
+    double r[ACC ? E : 1], q1[RK ? E : 1], qs[RK ? E : 1];
+};
+template <int NF, int ND, bool ACC, bool RK>
+__device__ __forceinline__ void load_cell(const SweepArgs &a, long long cell, CellIn<2*NF + ND + 1, ACC, RK> &in) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1;
     const long long fs = a.g.fstride;
-    double r[E];
+    if (ACC) {
+        const double *p = a.rhs + cell;
 #pragma unroll
-    for (int v = 0; v < E; v++) r[v] = a.first_dir ? 0.0 : a.rhs[v*fs + cell];
-    double q1[E], qs[E];
-    if (a.rk_mode != 0) {
-#pragma unroll
-        for (int v = 0; v < E; v++) q1[v] = a.q1[v*fs + cell];
+        for (int v = 0; v < E; v++) in.r[v] = __ldg(p + v*fs);
     }
-    if (a.rk_mode >= 2) {
+    if (RK) {
+#if MFC_STRICT
+        if (a.rk_mode != 0) {
+            const double *p = a.q1 + cell;
 #pragma unroll
-        for (int v = 0; v < E; v++) qs[v] = v >= ADV ? al[v - ADV] : a.q[v*fs + cell];
+            for (int v = 0; v < E; v++) in.q1[v] = __ldg(p + v*fs);
+        }
+        if (a.rk_mode >= 2) {
+            const double *p = a.q + cell;
+#pragma unroll
+            for (int v = 0; v < ADV; v++) in.qs[v] = __ldg(p + v*fs);
+        }
+#else
+        if (a.rk_mode >= 2) {
+            const double *p = a.q1 + cell;
+#pragma unroll
+            for (int v = 0; v < E; v++) in.q1[v] = __ldg(p + v*fs);
+        }
+#endif
     }
+}
+template <int NF, int ND, bool ACC, bool RK>
+__device__ __forceinline__ void prefetch_cell(const SweepArgs &a, long long cell) {
+    constexpr int E = 2*NF + ND + 1;
+    const long long fs = a.g.fstride;
+    if (ACC) {
+        const double *p = a.rhs + cell;
 #pragma unroll
-    for (int v = 0; v < E; v++) {
-        double x = rds*(Fm[v] - Fp[v]);
-        if (!a.first_dir) x = r[v] + x;
-        if (v >= ADV) x = x + rds*al[v - ADV]*(ufp - ufm);
-        if (a.rk_mode == 0) a.rhs[v*fs + cell] = x;
-        else a.qout[v*fs + cell] = rk_apply(a.rk_mode, q1[v], a.rk_mode >= 2 ? qs[v] : 0.0, x, a.dt);
+        for (int v = 0; v < E; v++) prefetch_l2(p + v*fs);
+    }
+    if (RK) {
+        if (a.rk_mode >= 2) {
+            const double *p = a.q1 + cell;
+#pragma unroll
+            for (int v = 0; v < E; v++) prefetch_l2(p + v*fs);
+        }
     }
 }
 
+// RHS of one cell + fused RK stage.  pc = the cell's entry in the ring (stride LD between
+// variables: partial densities and volume fractions as stored, velocities and pressure in
+// place of momenta and energy); in = the operands fetched by load_cell.
+template <int NF, int ND, int LD, bool ACC, bool RK>
+__device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell, double rds, const double *pc,
+                                             const CellIn<2*NF + ND + 1, ACC, RK> &in,
+                                             const double *Fm, double ufm, const double *Fp, double ufp) {
+    constexpr int E = 2*NF + ND + 1, MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+    const long long fs = a.g.fstride;
+    double x[E], al[NF];
+#pragma unroll
+    for (int i = 0; i < NF; i++) al[i] = pc[(ADV + i)*LD];
+    const double du = rds*(ufp - ufm);
+#pragma unroll
+    for (int v = 0; v < E; v++) {
+        x[v] = rds*(Fm[v] - Fp[v]);
+        if (ACC) x[v] = in.r[v] + x[v];
+        if (v >= ADV) {
+#if MFC_STRICT
+            x[v] = x[v] + rds*al[v - ADV]*(ufp - ufm);
+#else
+            x[v] = fma(al[v - ADV], du, x[v]);
+#endif
+        }
+    }
+    if (!RK || a.rk_mode == 0) {
+        double *o = a.rhs + cell;
+#pragma unroll
+        for (int v = 0; v < E; v++) o[v*fs] = x[v];
+        return;
+    }
+    double *o = a.qout + cell;
+#if MFC_STRICT
+#pragma unroll
+    for (int v = 0; v < E; v++) {
+        const double qs = a.rk_mode >= 2 ? (v >= ADV ? al[v - ADV] : in.qs[v]) : 0.0;
+        o[v*fs] = rk_apply(a.rk_mode, in.q1[v], qs, x[v], a.dt);
+    }
+#else
+    // stage state rebuilt from the ring
+    double qs[E], rho = 0.0, gamma = 0.0, pi_inf = 0.0, v2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        qs[i] = pc[i*LD];
+        qs[ADV + i] = al[i];
+        rho += qs[i];
+        gamma = fma(al[i], a.gammas[i], gamma);
+        pi_inf = fma(al[i], a.pi_infs[i], pi_inf);
+    }
+    rho = fmax(rho, 1e-16);
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        const double u = pc[(MOM + i)*LD];
+        qs[MOM + i] = rho*u;
+        v2 = fma(u, u, v2);
+    }
+    qs[EN] = fma(gamma, pc[EN*LD], pi_inf) + 5e-1*rho*v2;
+    // every TVD-RK statement is (c1 q1 + c2 qs + c3 dt rhs)*c4   (m_time_steppers.fpp:167,245,322,342)
+    const int m = a.rk_mode;
+    const double c1 = m == 3 ? 3.0 : 1.0, c2 = m == 1 ? 0.0 : (m == 4 ? 2.0 : 1.0);
+    const double c3 = (m == 4 ? 2.0 : 1.0)*a.dt, c4 = m == 1 ? 1.0 : (m == 2 ? 0.5 : (m == 3 ? 0.25 : 1.0/3.0));
+#pragma unroll
+    for (int v = 0; v < E; v++) {
+        const double q1 = m == 1 ? qs[v] : in.q1[v];
+        o[v*fs] = fma(c1, q1, fma(c2, qs[v], c3*x[v]))*c4;
+    }
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
-// x sweep, v2.  A CTA of 4 warps owns 120 consecutive cells of a row and streams `rows`
-// consecutive rows through a 4-slot ring (one bulk copy of 128 doubles per variable and row,
-// issued by one thread, three rows ahead of the compute).  Within a row the work is the warp
-// shuffle pencil of v1: lane = cell, neighbours' face states / fluxes by shuffle.
+// x sweep, v2.  Every WARP is an independent pipeline: it owns 30 consecutive cells of a row
+// and streams `rows` consecutive rows through its private 4-slot ring (one 320-byte bulk copy
+// per variable and row, issued by lane 0 three rows ahead of the compute; mbarrier per slot).
+// No block-wide barrier exists, so warps never wait for each other.  Within a row the work is
+// the warp-shuffle pencil of v1: lane = cell, neighbours' face states / fluxes by shuffle.
+// BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int COEF>
+template <int NF, int ND, int COEF, bool BC4>
 __global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = E*kTX;
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = E*kWX;
+    constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *ring = reinterpret_cast<double *>(smem_raw);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ring + R*SLOT);
     const GridDesc &g = a.g;
-    const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
-    const int j0 = blockIdx.x*(4*kWarpCells);          // first cell finished by this CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsPerCta*R*SLOT) + warp*R;
+    const int jw = (blockIdx.x*kWarpsPerCta + warp)*kWarpCells;   // first cell finished by this warp
+    if (jw > g.N[0]) return;                           // whole warp out of range (no block barriers below)
     const int k0 = blockIdx.y*a.rows, l = blockIdx.z;
     const int nrows = min(a.rows, g.N[1] + 1 - k0);
-    const int x0 = j0 - 4;                             // first staged column
-    const int nx = min(kTX, g.pitch - (x0 + kXoff));   // staged doubles per row (even)
+    const int x0 = jw - 4;                             // first staged column
+    const int nx = min(kWX, g.pitch - (x0 + kXoff));   // staged doubles per row (even)
     const unsigned row_bytes = (unsigned)nx*8u;
     const long long fs = g.fstride;
     const long long base = g.at(x0, k0, l);
-    if (tx == 0) {
+    if (lane == 0) {
         for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncwarp();
     auto issue = [&](int r) {
         const int slot = r & (R - 1);
         mbar_expect_tx(&bar[slot], row_bytes*E);
 #pragma unroll
         for (int v = 0; v < E; v++)
-            bulk_g2s(ring + slot*SLOT + v*kTX, a.q + v*fs + base + (long long)r*g.sy, row_bytes, &bar[slot]);
+            bulk_g2s(ring + slot*SLOT + v*kWX, a.q + v*fs + base + (long long)r*g.sy, row_bytes, &bar[slot]);
     };
-    if (tx == 0)
+    if (lane == 0)
         for (int r = 0; r < min(R, nrows); r++) issue(r);
 
-    const int jw = j0 + warp*kWarpCells;               // first cell finished by this warp
-    const bool warp_on = jw <= g.N[0];
     const int j_raw = jw - 1 + lane;
     const int j = min(j_raw, g.N[0] + 1);              // clamped lanes never store
-    const int sx = j - x0;                             // staged index of my cell (3 .. 124)
+    const int sx = j - x0;                             // staged index of my cell (3 .. 34)
     double c[27];
     get_coef<COEF>(a, j, c);
     const double rds = a.rds[j + g.b];
     const unsigned full = 0xffffffffu;
-    const bool conv_on = tx < nx;
+    const bool store_on = lane >= 1 && lane <= kWarpCells && j_raw <= g.N[0];
+    const bool stab_on = a.stab_out != nullptr;
+    double icfl = 0.0;
 
     for (int r = 0; r < nrows; r++) {
         const int slot = r & (R - 1);
         double *row = ring + slot*SLOT;
         mbar_wait(&bar[slot], (unsigned)(r/R) & 1u);
-        if (conv_on) prim_in_place<NF, ND>(row + tx, a.gammas, a.pi_infs);
-        fence_proxy_async();
-        __syncthreads();                               // row converted; everyone is done with row r-1
-        if (tx == 0 && r >= 1 && r - 1 + R < nrows) issue(r - 1 + R);
-        if (!warp_on) continue;
+        if (lane < nx) prim_in_place<NF, ND, kWX>(row + lane, a.gammas, a.pi_infs);
+        if (lane + 32 < nx) prim_in_place<NF, ND, kWX>(row + lane + 32, a.gammas, a.pi_infs);
+        __syncwarp();
+        const long long cell = g.at(j, k0 + r, l);
+        CellIn<E, ACC, RK> in;
+        if (store_on) load_cell<NF, ND, ACC, RK>(a, cell, in);
         const double *p = row + sx;
         double vL[E], vR[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
             double s[5];
 #pragma unroll
-            for (int t = 0; t < 5; t++) s[t] = p[v*kTX + (t - 2)];
+            for (int t = 0; t < 5; t++) s[t] = p[v*kWX + (t - 2)];
             weno5(s, c, a.eps, vL[v], vR[v]);
         }
-        double Ls[E], Rs[E];
+        double pc[E];                                  // my cell's ring entry, kept for the finish
 #pragma unroll
-        for (int v = 0; v < E; v++) {
-            Ls[v] = vR[v];
-            Rs[v] = __shfl_down_sync(full, vL[v], 1);
+        for (int v = 0; v < E; v++) pc[v] = (RK || v >= ADV || stab_on) ? p[v*kWX] : 0.0;
+#if !MFC_STRICT
+        if (stab_on && store_on) {                     // ICFL, m_data_output.fpp:215-233 (inviscid)
+            double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                rho += pc[i];
+                gamma = fma(pc[ADV + i], a.gammas[i], gamma);
+                pi_inf = fma(pc[ADV + i], a.pi_infs[i], pi_inf);
+            }
+            const double cs = sqrt_ratio_fast(fma(gamma + 1.0, pc[NF + ND], pi_inf), gamma*rho);
+            // dt/min_d(ds_d/(|u_d| + c)) = dt max_d((|u_d| + c)/ds_d)
+            double m = (fabs(pc[NF]) + cs)*rds;
+            if (ND >= 2) m = fmax(m, (fabs(pc[NF + (ND >= 2 ? 1 : 0)]) + cs)*__ldg(a.rds_t[0] + k0 + r + g.b));
+            if (ND >= 3) m = fmax(m, (fabs(pc[NF + (ND >= 3 ? 2 : 0)]) + cs)*__ldg(a.rds_t[1] + l + g.b));
+            icfl = fmax(icfl, a.dt*m);
         }
-        if (a.bc_beg == -4 && j_raw == -1) {           // m_riemann_solvers.fpp:480-487
+#endif
+        fence_proxy_async();
+        __syncwarp();                                  // the warp is done with this slot
+        if (lane == 0 && r + R < nrows) issue(r + R);
+        double Rs[E];
 #pragma unroll
-            for (int v = 0; v < E; v++) Ls[v] = Rs[v];
-        }
-        if (a.bc_end == -4 && j_raw == g.N[0]) {       // :515-523
+        for (int v = 0; v < E; v++) Rs[v] = __shfl_down_sync(full, vL[v], 1);
+        if (BC4) {
+            if (a.bc_beg == -4 && j_raw == -1) {       // m_riemann_solvers.fpp:480-487
 #pragma unroll
-            for (int v = 0; v < E; v++) Rs[v] = Ls[v];
+                for (int v = 0; v < E; v++) vR[v] = Rs[v];
+            }
+            if (a.bc_end == -4 && j_raw == g.N[0]) {   // :515-523
+#pragma unroll
+                for (int v = 0; v < E; v++) Rs[v] = vR[v];
+            }
         }
         double F[E], uf;
-        hllc<NF, ND, 0>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+        hllc<NF, ND, 0>(vR, Rs, a.gammas, a.pi_infs, F, uf);
         double Fm[E], ufm;
 #pragma unroll
         for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
         ufm = __shfl_up_sync(full, uf, 1);
-        if (lane >= 1 && lane <= kWarpCells && j_raw <= g.N[0]) {
-            double al[NF];
+        if (store_on) finish_cell2<NF, ND, 1, ACC, RK>(a, cell, rds, pc, in, Fm, ufm, F, uf);
+    }
+    if (stab_on) {                                     // all values >= 0: the bit pattern orders like the value
+        unsigned long long b = (unsigned long long)__double_as_longlong(icfl);
 #pragma unroll
-            for (int i = 0; i < NF; i++) al[i] = p[(ADV + i)*kTX];
-            finish_cell2<NF, ND>(a, g.at(j, k0 + r, l), rds, al, Fm, ufm, F, uf);
-        }
+        for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(full, b, o));
+        if (lane == 0) atomicMax(a.stab_out, b);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// y / z sweep, v2.  A CTA owns 128 consecutive x columns at one transverse index and marches
-// a pencil segment s0..s1 along the sweep direction.  Rows s0-3 .. s1+3 stream through an
-// 8-slot ring (5 live rows of the stencil + 3 rows in flight); every thread converts, reads
-// and reconstructs only its own column, carrying the previous cell's right-face state and the
-// previous face's flux in registers as in v1, so the only block-wide synchronisation is the
-// slot hand-back once per row.
+// y / z sweep, v2.  Every WARP is an independent pipeline: it owns 32 consecutive x columns at
+// one transverse index and marches a pencil segment s0..s1 along the sweep direction.  Rows
+// s0-3 .. s1+3 stream through the warp's private 8-slot ring (5 live rows of the stencil + 3
+// rows in flight, one 256-byte bulk copy per variable and row); every lane converts, reads and
+// reconstructs only its own column, carrying the previous cell's right-face state and the
+// previous face's flux in registers, so the only synchronisation is a __syncwarp before a slot
+// is handed back to the TMA engine.
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR, int COEF>
+template <int NF, int ND, int DIR, int COEF, bool BC4>
 __global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingY, SLOT = E*kTX;
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingY, SLOT = E*kWY;
+    constexpr bool ACC = true, RK = DIR == ND - 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *ring = reinterpret_cast<double *>(smem_raw);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ring + R*SLOT);
     const GridDesc &g = a.g;
-    const int tx = threadIdx.x;
-    const int j0 = blockIdx.x*kTX, j = j0 + tx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsPerCta*R*SLOT) + warp*R;
+    const int j0 = (blockIdx.x*kWarpsPerCta + warp)*kWY, j = j0 + lane;
+    if (j0 > g.N[0]) return;                           // whole warp out of range
     const int t = blockIdx.z;
     const int s0 = blockIdx.y*a.seg;
     const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
     const bool on = j <= g.N[0];
     const long long ss = DIR == 1 ? g.sy : g.sz;
-    const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the tile
-    const int nx = min(kTX, g.pitch - (j0 + kXoff));
+    const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the warp's columns
+    const int nx = min(kWY, g.pitch - (j0 + kXoff));
     const unsigned row_bytes = (unsigned)nx*8u;
     const long long fs = g.fstride;
     const int r_first = s0 - 3, r_last = s1 + 3;
-    if (tx == 0) {
+    if (lane == 0) {
         for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncwarp();
     auto issue = [&](int r) {
         const int slot = (r - r_first) & (R - 1);
         mbar_expect_tx(&bar[slot], row_bytes*E);
 #pragma unroll
         for (int v = 0; v < E; v++)
-            bulk_g2s(ring + slot*SLOT + v*kTX, a.q + v*fs + base + (long long)r*ss, row_bytes, &bar[slot]);
+            bulk_g2s(ring + slot*SLOT + v*kWY, a.q + v*fs + base + (long long)r*ss, row_bytes, &bar[slot]);
     };
-    int next_issue = r_first + R;                      // only thread 0 issues, everyone counts
-    if (tx == 0)
+    int next_issue = r_first + R;                      // only lane 0 issues, every lane counts
+    if (lane == 0)
         for (int r = r_first; r < r_first + R && r <= r_last; r++) issue(r);
 
     int conv = r_first;                                // next row to wait for and convert
     double vRp[E], Fp[E], ufp = 0.0;
 #pragma unroll
     for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
-    const long long col = base + tx;
+    const long long col = base + lane;
     for (int s = s0 - 1; s <= s1 + 1; s++) {
         while (conv <= s + 2) {
             const int i = conv - r_first, slot = i & (R - 1);
             mbar_wait(&bar[slot], (unsigned)(i/R) & 1u);
-            if (on) prim_in_place<NF, ND>(ring + slot*SLOT + tx, a.gammas, a.pi_infs);
+            if (on) prim_in_place<NF, ND, kWY>(ring + slot*SLOT + lane, a.gammas, a.pi_infs);
             conv++;
         }
+        const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
+        const long long cellm = col + (long long)(s - 1)*ss;
+        if (on && s <= s1) prefetch_cell<NF, ND, ACC, RK>(a, cellm + ss);   // operands of the NEXT iteration's finish
         if (on) {
             double c[27];
             get_coef<COEF>(a, s, c);
             const double *p[5];
 #pragma unroll
-            for (int q = 0; q < 5; q++) p[q] = ring + ((s - 2 + q - r_first) & (R - 1))*SLOT + tx;
+            for (int q = 0; q < 5; q++) p[q] = ring + ((s - 2 + q - r_first) & (R - 1))*SLOT + lane;
             double vL[E], vR[E];
 #pragma unroll
             for (int v = 0; v < E; v++) {
                 double st[5];
 #pragma unroll
-                for (int q = 0; q < 5; q++) st[q] = p[q][v*kTX];
+                for (int q = 0; q < 5; q++) st[q] = p[q][v*kWY];
                 weno5(st, c, a.eps, vL[v], vR[v]);
             }
             if (s >= s0) {
-                double Ls[E], Rs[E];
+                CellIn<E, ACC, RK> in;
+                if (fin) load_cell<NF, ND, ACC, RK>(a, cellm, in);
+                if (BC4) {
+                    if (a.bc_beg == -4 && s == 0) {
 #pragma unroll
-                for (int v = 0; v < E; v++) { Ls[v] = vRp[v]; Rs[v] = vL[v]; }
-                if (a.bc_beg == -4 && s == 0) {
+                        for (int v = 0; v < E; v++) vRp[v] = vL[v];
+                    }
+                    if (a.bc_end == -4 && s == g.N[DIR] + 1) {
 #pragma unroll
-                    for (int v = 0; v < E; v++) Ls[v] = Rs[v];
-                }
-                if (a.bc_end == -4 && s == g.N[DIR] + 1) {
-#pragma unroll
-                    for (int v = 0; v < E; v++) Rs[v] = Ls[v];
+                        for (int v = 0; v < E; v++) vL[v] = vRp[v];
+                    }
                 }
                 double F[E], uf;
-                hllc<NF, ND, DIR>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
-                if (s >= s0 + 1) {
-                    double al[NF];
-#pragma unroll
-                    for (int i = 0; i < NF; i++) al[i] = p[1][(ADV + i)*kTX];      // row s-1
-                    finish_cell2<NF, ND>(a, col + (long long)(s - 1)*ss, a.rds[s - 1 + g.b], al, Fp, ufp, F, uf);
-                }
+                hllc<NF, ND, DIR>(vRp, vL, a.gammas, a.pi_infs, F, uf);
+                if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, cellm, a.rds[s - 1 + g.b], p[1], in, Fp, ufp, F, uf);   // p[1]: row s-1
 #pragma unroll
                 for (int v = 0; v < E; v++) Fp[v] = F[v];
                 ufp = uf;
@@ -719,9 +853,9 @@ __global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ Sweep
             for (int v = 0; v < E; v++) vRp[v] = vR[v];
         }
         fence_proxy_async();
-        __syncthreads();                               // row s-2 is dead for the whole CTA
+        __syncwarp();                                  // row s-2 is dead for the whole warp
         if (next_issue <= r_last) {
-            if (tx == 0) issue(next_issue);
+            if (lane == 0) issue(next_issue);
             next_issue++;
         }
     }

@@ -76,7 +76,8 @@ struct Sim {
     int variant = 2;                   // sweep kernel generation (MFC_B200_KERNELS=1 selects the v1 kernels)
     double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr};
     std::vector<double> h_coef[3];
-    unsigned long long *stab_dev = nullptr, *stab_host = nullptr;
+    unsigned long long *stab_dev = nullptr, *stab_host = nullptr, *stab_init = nullptr;
+    bool stab_pending = false;
     int bc[3][2];                      // effective codes: self-neighbours folded into periodic
     double *sendbuf[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     double *recvbuf[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -141,6 +142,7 @@ void free_all() {
     }
     if (S.stab_dev) { cudaFree(S.stab_dev); S.stab_dev = nullptr; }
     if (S.stab_host) { cudaFreeHost(S.stab_host); S.stab_host = nullptr; }
+    if (S.stab_init) { cudaFreeHost(S.stab_init); S.stab_init = nullptr; }
     if (S.ev0) { cudaEventDestroy(S.ev0); S.ev0 = nullptr; }
     if (S.ev1) { cudaEventDestroy(S.ev1); S.ev1 = nullptr; }
     if (S.sv0) { cudaEventDestroy(S.sv0); S.sv0 = nullptr; }
@@ -202,52 +204,70 @@ int run_prim(const double *q) {
     return 0;
 }
 
-int run_stability(const double *q, double dt, double stab[3]) {
+// stability criteria (m_data_output.fpp:197-274): everything is ENQUEUED on the stream; the
+// host reads the result in stab_fetch() after the step's single synchronisation.
+int stab_reset() {
+    const double inf = INFINITY;
+    unsigned long long init[3] = {0ull, 0ull, 0ull};
+    std::memcpy(&init[2], &inf, sizeof(double));
+    std::memcpy(S.stab_init, init, sizeof(init));
+    CK(cudaMemcpyAsync(S.stab_dev, S.stab_init, sizeof(init), cudaMemcpyHostToDevice, S.st));
+    return 0;
+}
+int stab_reduce_and_copy() {
+    if (S.comm) {   // m_mpi_common.fpp:155-165: MAX / MIN over ranks (every rank gets the result)
+        NK(S.nccl.AllReduce(S.stab_dev, S.stab_dev, 2, ncclUint64, ncclMax, S.comm, S.st));
+        NK(S.nccl.AllReduce(S.stab_dev + 2, S.stab_dev + 2, 1, ncclUint64, ncclMin, S.comm, S.st));
+    }
+    CK(cudaMemcpyAsync(S.stab_host, S.stab_dev, 3*sizeof(unsigned long long), cudaMemcpyDeviceToHost, S.st));
+    S.stab_pending = true;
+    return 0;
+}
+int run_stability(const double *q, double dt) {
+    int rc;
     // the v2 sweeps convert in shared memory; q_prim_vf is materialised only for this diagnostic
-    if (S.variant == 2) { int rc = run_prim(q); if (rc) return rc; }
+    if (S.variant == 2 && (rc = run_prim(q))) return rc;
+    if ((rc = stab_reset())) return rc;
     StabArgs a{};
     a.g = S.g; a.q = q; a.prim = S.prim; a.dt = dt; a.out = S.stab_dev;
     for (int d = 0; d < 3; d++) a.ds[d] = S.ds[d];
     for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
     a.Re_size[0] = a.Re_size[1] = 0;
-    const double inf = INFINITY;
-    unsigned long long init[3] = {0ull, 0ull, 0ull};
-    std::memcpy(&init[2], &inf, sizeof(double));
-    std::memcpy(S.stab_host, init, sizeof(init));
-    CK(cudaMemcpyAsync(S.stab_dev, S.stab_host, sizeof(init), cudaMemcpyHostToDevice, S.st));
     {
         Scope sc(KC_STAB); sc.done(S.L->stability(S.nf, S.nd, a, S.st));
     }
-    if (S.comm) {   // m_mpi_common.fpp:155-165: MAX / MIN over ranks (every rank gets the result)
-        NK(S.nccl.AllReduce(S.stab_dev, S.stab_dev, 2, ncclUint64, ncclMax, S.comm, S.st));
-        NK(S.nccl.AllReduce(S.stab_dev + 2, S.stab_dev + 2, 1, ncclUint64, ncclMin, S.comm, S.st));
-    }
-    CK(cudaMemcpyAsync(S.stab_host, S.stab_dev, sizeof(init), cudaMemcpyDeviceToHost, S.st));
-    CK(cudaStreamSynchronize(S.st));
-    if (stab) {
-        std::memcpy(&stab[0], &S.stab_host[0], sizeof(double));
-        if (S.viscous) { std::memcpy(&stab[1], &S.stab_host[1], sizeof(double)); std::memcpy(&stab[2], &S.stab_host[2], sizeof(double)); }
-    }
-    return 0;
+    return stab_reduce_and_copy();
+}
+// after the stream has been synchronised
+void stab_fetch(double stab[3]) {
+    if (!S.stab_pending) return;
+    S.stab_pending = false;
+    if (!stab) return;
+    std::memcpy(&stab[0], &S.stab_host[0], sizeof(double));
+    if (S.viscous) { std::memcpy(&stab[1], &S.stab_host[1], sizeof(double)); std::memcpy(&stab[2], &S.stab_host[2], sizeof(double)); }
 }
 
 // one s_compute_rhs on the stage state q (ghosts rebuilt in place), followed -- fused into the
 // last sweep -- by the RK statement rk_mode writes into qout
 int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt, int t_step,
-              bool first_stage, double stab[3]) {
+              bool first_stage, bool want_stab) {
     int rc;
     const bool stop = first_stage && t_step == S.p.t_step_stop;
     // Reference quirk, kept: at t_step == t_step_stop s_compute_rhs returns (m_rhs.fpp:452)
     // BEFORE it refreshes q_prim_vf (:659-675), so the last run_time.inf row is computed from
     // the primitive variables of the previous RHS evaluation (m_time_steppers.fpp:288-290).
-    if (stop && S.p.run_time_info && stab && S.last_q)
-        if ((rc = run_stability(S.last_q, dt, stab))) return rc;
+    if (stop && S.p.run_time_info && want_stab && S.last_q)
+        if ((rc = run_stability(S.last_q, dt))) return rc;
     if ((rc = fill_ghosts(q))) return rc;                    // m_rhs.fpp:435
     if (S.variant != 2 && (rc = run_prim(q))) return rc;     // :445-447 (v2: fused into the sweeps)
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
     S.last_q = q;
-    if (first_stage && S.p.run_time_info && stab)            // m_time_steppers.fpp:288-290
-        if ((rc = run_stability(q, dt, stab))) return rc;
+    // m_time_steppers.fpp:288-290.  Inviscid fast build: the ICFL maximum is taken by the x sweep
+    // itself from the primitive variables it already holds (no extra pass over the state).
+    const bool do_stab = first_stage && S.p.run_time_info && want_stab;
+    const bool fuse_stab = do_stab && S.variant == 2 && !S.p.strict_math && !S.viscous;
+    if (do_stab && !fuse_stab && (rc = run_stability(q, dt))) return rc;
+    if (fuse_stab && (rc = stab_reset())) return rc;
     for (int d = 0; d < S.nd; d++) {                         // :469
         SweepArgs a{};
         a.g = S.g; a.q = q; a.prim = S.prim; a.rhs = S.rhs; a.q1 = q1; a.qout = qout;
@@ -258,16 +278,19 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.first_dir = d == 0;
         a.rk_mode = d == S.nd - 1 ? rk_mode : 0;
         a.variant = S.variant; a.coef_uniform = S.coef_uniform[d];
+        a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
+        a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
         Scope sc(KC_SWEEP_X + d);
         const int n = S.L->sweep(S.nf, S.nd, d, a, S.st);
         if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
         sc.done(n);
+        if (fuse_stab && d == 0 && (rc = stab_reduce_and_copy())) return rc;
     }
     return 0;
 }
 
-int do_step(int t_step, double dt, double stab[3]) {
+int do_step(int t_step, double dt, bool stab) {
     double *q1 = S.state[S.cur], *A = S.state[(S.cur + 1) % 3], *B = S.state[(S.cur + 2) % 3];
     int rc;
     const int ts = S.p.time_stepper;
@@ -277,12 +300,12 @@ int do_step(int t_step, double dt, double stab[3]) {
     } else if (ts == 2) {                                                  // :197-267
         if ((rc = rhs_stage(q1, 1, q1, A, dt, t_step, true, stab))) return rc;
         if (t_step == S.p.t_step_stop) return 0;
-        if ((rc = rhs_stage(A, 2, q1, q1, dt, t_step, false, nullptr))) return rc;
+        if ((rc = rhs_stage(A, 2, q1, q1, dt, t_step, false, false))) return rc;
     } else {                                                               // :271-362
         if ((rc = rhs_stage(q1, 1, q1, A, dt, t_step, true, stab))) return rc;
         if (t_step == S.p.t_step_stop) return 0;
-        if ((rc = rhs_stage(A, 3, q1, B, dt, t_step, false, nullptr))) return rc;
-        if ((rc = rhs_stage(B, 4, q1, q1, dt, t_step, false, nullptr))) return rc;
+        if ((rc = rhs_stage(A, 3, q1, B, dt, t_step, false, false))) return rc;
+        if ((rc = rhs_stage(B, 4, q1, q1, dt, t_step, false, false))) return rc;
     }
     return 0;
 }
@@ -372,6 +395,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     CK(cudaMalloc(&S.rhs, sb)); CK(cudaMemsetAsync(S.rhs, 0, sb, S.st));
     CK(cudaMalloc(&S.stab_dev, 3*sizeof(unsigned long long)));
     CK(cudaMallocHost(&S.stab_host, 3*sizeof(unsigned long long)));
+    CK(cudaMallocHost(&S.stab_init, 3*sizeof(unsigned long long)));
     for (int d = 0; d < nd; d++) {
         const int N = S.g.N[d], b = S.b;
         WenoTable t = build_weno5_table(p->cb[d], N, b);
@@ -467,12 +491,12 @@ int mfc_b200_download_prim(double *const q_prim[]) {
 int mfc_b200_step(int t_step, double dt, double stab[3], double *step_seconds) {
     if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step before mfc_b200_upload");
     CK(cudaEventRecord(S.sv0, S.st));
-    double local[3] = {0, 0, 0};
-    int rc = do_step(t_step, dt, S.p.run_time_info ? (stab ? stab : local) : nullptr);
+    int rc = do_step(t_step, dt, S.p.run_time_info != 0);
     if (rc) return rc;
     CK(cudaEventRecord(S.sv1, S.st));
     CK(cudaStreamSynchronize(S.st));
     CK(cudaGetLastError());
+    stab_fetch(stab);
     if (step_seconds) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, S.sv0, S.sv1)); *step_seconds = ms*1e-3; }
     return 0;
 }
@@ -480,7 +504,7 @@ int mfc_b200_step(int t_step, double dt, double stab[3], double *step_seconds) {
 int mfc_b200_step_async(int t_step, double dt, int n_steps) {
     if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step_async before mfc_b200_upload");
     for (int s = 0; s < n_steps; s++) {
-        int rc = do_step(t_step + s, dt, nullptr);
+        int rc = do_step(t_step + s, dt, false);
         if (rc) return rc;
     }
     return 0;
@@ -499,7 +523,7 @@ int mfc_b200_compute_rhs(const double *const q_cons[], double *const rhs[]) {
     int rc;
     for (int v = 0; v < S.E; v++)
         if ((rc = copy_field(scratch + (size_t)v*S.g.fstride, q_cons[v], true, S.st))) return rc;
-    if ((rc = rhs_stage(scratch, 0, scratch, scratch, 0.0, S.p.t_step_stop - 1, false, nullptr))) return rc;
+    if ((rc = rhs_stage(scratch, 0, scratch, scratch, 0.0, S.p.t_step_stop - 1, false, false))) return rc;
     const GridDesc &g = S.g;
     const size_t w = (size_t)(g.N[0] + 1)*sizeof(double);
     for (int v = 0; v < S.E; v++)
