@@ -16,7 +16,7 @@ import numpy as np
 MAX_FLUIDS = 4
 ABI_VERSION = 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfc_b200.so")
+LIB_PATH = os.environ.get("MFC_B200_LIB") or os.path.join(_HERE, "libmfc_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 

@@ -17,6 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmfc_b200.so")
+# tuning builds (tools/tune_variants.py): extra -D flags and an alternative output name
+EXTRA_DEFS = os.environ.get("MFC_B200_DEFS", "").split()
+if os.environ.get("MFC_B200_LIBNAME"):
+    LIB = os.path.join(HERE, os.environ["MFC_B200_LIBNAME"])
+    OBJ = os.path.join(CSRC, "build_" + os.environ["MFC_B200_LIBNAME"].replace(".", "_"))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
@@ -55,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + EXTRA_DEFS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

@@ -448,10 +448,26 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 constexpr int kWX = 40;        // doubles staged per warp, row and variable by the x kernel (36 used)
 constexpr int kWY = 32;        // columns per warp in the y/z march
-constexpr int kRingY = 8;      // row slots of the y/z march ring: 5 live rows + 3 in flight
-constexpr int kRingX = 4;      // row slots of the x kernel: 1 live row + 3 in flight
+// tuning knobs (tools/tune_variants.py builds and times alternatives)
+#ifndef MFC_RING_Y
+#define MFC_RING_Y 6
+#define MFC_WARPS_Y 4
+#define MFC_CTAS_Y 4
+#endif
+#ifndef MFC_RING_X
+#define MFC_RING_X 4
+#define MFC_WARPS_X 4
+#define MFC_CTAS_X 5
+#endif
+constexpr int kRingY = MFC_RING_Y;   // row slots of the y/z march ring: 5 live rows + the rows in flight
+constexpr int kRingX = MFC_RING_X;   // row slots of the x kernel: 1 live row + the rows in flight
 constexpr int kWarpCells = 30; // cells finished per warp and row in the x kernel
-constexpr int kWarpsPerCta = 4;
+// Occupancy (measured at 512^3, profiles/r01_tune_occupancy.txt): x 5 CTAs x 4 warps (<= 96
+// registers, 40 KB of rings per CTA), y/z 4 CTAs x 4 warps (<= 128 registers, 6-slot rings,
+// 48 KB per CTA) is the fastest of the variants tried; 15 or 18 warps per SM with fewer
+// registers are slower.
+constexpr int kWarpsX = MFC_WARPS_X, kCtasX = MFC_CTAS_X;
+constexpr int kWarpsY = MFC_WARPS_Y, kCtasY = MFC_CTAS_Y;
 
 // cons -> prim of one cell held in a ring slot (stride LD between variables), in place:
 // momenta become velocities, the energy becomes the pressure (:187-227, :353-362, :98-106)
@@ -640,15 +656,15 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell,
 // BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int COEF, bool BC4>
-__global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = E*kWX;
     constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsPerCta*R*SLOT) + warp*R;
-    const int jw = (blockIdx.x*kWarpsPerCta + warp)*kWarpCells;   // first cell finished by this warp
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsX*R*SLOT) + warp*R;
+    const int jw = (blockIdx.x*kWarpsX + warp)*kWarpCells;   // first cell finished by this warp
     if (jw > g.N[0]) return;                           // whole warp out of range (no block barriers below)
     const int k0 = blockIdx.y*a.rows, l = blockIdx.z;
     const int nrows = min(a.rows, g.N[1] + 1 - k0);
@@ -662,15 +678,14 @@ __global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepAr
         mbar_fence_init();
     }
     __syncwarp();
-    auto issue = [&](int r) {
-        const int slot = r & (R - 1);
+    auto issue = [&](int r, int slot) {
         mbar_expect_tx(&bar[slot], row_bytes*E);
 #pragma unroll
         for (int v = 0; v < E; v++)
             bulk_g2s(ring + slot*SLOT + v*kWX, a.q + v*fs + base + (long long)r*g.sy, row_bytes, &bar[slot]);
     };
     if (lane == 0)
-        for (int r = 0; r < min(R, nrows); r++) issue(r);
+        for (int r = 0; r < min(R, nrows); r++) issue(r, r);
 
     const int j_raw = jw - 1 + lane;
     const int j = min(j_raw, g.N[0] + 1);              // clamped lanes never store
@@ -683,10 +698,11 @@ __global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepAr
     const bool stab_on = a.stab_out != nullptr;
     double icfl = 0.0;
 
+    int slot = 0;
+    unsigned phase = 0;
     for (int r = 0; r < nrows; r++) {
-        const int slot = r & (R - 1);
         double *row = ring + slot*SLOT;
-        mbar_wait(&bar[slot], (unsigned)(r/R) & 1u);
+        mbar_wait(&bar[slot], phase);
         if (lane < nx) prim_in_place<NF, ND, kWX>(row + lane, a.gammas, a.pi_infs);
         if (lane + 32 < nx) prim_in_place<NF, ND, kWX>(row + lane + 32, a.gammas, a.pi_infs);
         __syncwarp();
@@ -724,7 +740,8 @@ __global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepAr
 #endif
         fence_proxy_async();
         __syncwarp();                                  // the warp is done with this slot
-        if (lane == 0 && r + R < nrows) issue(r + R);
+        if (lane == 0 && r + R < nrows) issue(r + R, slot);
+        if (++slot == R) { slot = 0; phase ^= 1u; }
         double Rs[E];
 #pragma unroll
         for (int v = 0; v < E; v++) Rs[v] = __shfl_down_sync(full, vL[v], 1);
@@ -764,15 +781,15 @@ __global__ void __launch_bounds__(128, 4) k_xrow(const __grid_constant__ SweepAr
 // is handed back to the TMA engine.
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int DIR, int COEF, bool BC4>
-__global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingY, SLOT = E*kWY;
+__global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1, R = kRingY, SLOT = E*kWY;
     constexpr bool ACC = true, RK = DIR == ND - 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsPerCta*R*SLOT) + warp*R;
-    const int j0 = (blockIdx.x*kWarpsPerCta + warp)*kWY, j = j0 + lane;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsY*R*SLOT) + warp*R;
+    const int j0 = (blockIdx.x*kWarpsY + warp)*kWY, j = j0 + lane;
     if (j0 > g.N[0]) return;                           // whole warp out of range
     const int t = blockIdx.z;
     const int s0 = blockIdx.y*a.seg;
@@ -789,8 +806,7 @@ __global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ Sweep
         mbar_fence_init();
     }
     __syncwarp();
-    auto issue = [&](int r) {
-        const int slot = (r - r_first) & (R - 1);
+    auto issue = [&](int r, int slot) {
         mbar_expect_tx(&bar[slot], row_bytes*E);
 #pragma unroll
         for (int v = 0; v < E; v++)
@@ -798,19 +814,22 @@ __global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ Sweep
     };
     int next_issue = r_first + R;                      // only lane 0 issues, every lane counts
     if (lane == 0)
-        for (int r = r_first; r < r_first + R && r <= r_last; r++) issue(r);
+        for (int r = r_first; r < r_first + R && r <= r_last; r++) issue(r, r - r_first);
 
-    int conv = r_first;                                // next row to wait for and convert
+    // ring bookkeeping (R need not be a power of two): slot of row s-2, and slot / phase of the
+    // next row to wait for and convert
+    int slot_lo = 0, conv = r_first, slot_cv = 0;
+    unsigned phase_cv = 0;
     double vRp[E], Fp[E], ufp = 0.0;
 #pragma unroll
     for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
     const long long col = base + lane;
     for (int s = s0 - 1; s <= s1 + 1; s++) {
         while (conv <= s + 2) {
-            const int i = conv - r_first, slot = i & (R - 1);
-            mbar_wait(&bar[slot], (unsigned)(i/R) & 1u);
-            if (on) prim_in_place<NF, ND, kWY>(ring + slot*SLOT + lane, a.gammas, a.pi_infs);
+            mbar_wait(&bar[slot_cv], phase_cv);
+            if (on) prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
             conv++;
+            if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
         }
         const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
         const long long cellm = col + (long long)(s - 1)*ss;
@@ -820,7 +839,10 @@ __global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ Sweep
             get_coef<COEF>(a, s, c);
             const double *p[5];
 #pragma unroll
-            for (int q = 0; q < 5; q++) p[q] = ring + ((s - 2 + q - r_first) & (R - 1))*SLOT + lane;
+            for (int q = 0; q < 5; q++) {
+                const int sl = slot_lo + q;
+                p[q] = ring + (sl >= R ? sl - R : sl)*SLOT + lane;
+            }
             double vL[E], vR[E];
 #pragma unroll
             for (int v = 0; v < E; v++) {
@@ -855,9 +877,10 @@ __global__ void __launch_bounds__(128, 3) k_march2(const __grid_constant__ Sweep
         fence_proxy_async();
         __syncwarp();                                  // row s-2 is dead for the whole warp
         if (next_issue <= r_last) {
-            if (lane == 0) issue(next_issue);
+            if (lane == 0) issue(next_issue, slot_lo);
             next_issue++;
         }
+        if (++slot_lo == R) slot_lo = 0;
     }
 }
 

@@ -1,0 +1,78 @@
+"""Worker of tests/test_multigpu.py: launched with torch.distributed.run, one rank per GPU.
+Every rank drives libmfc_b200.so on its block of the reference's domain decomposition; the
+halo exchange is the library's NCCL send/recv path.  Rank 0 gathers the blocks and compares
+them with the single-rank CPU oracle (strict mode: bitwise; fast mode: <= 1e-10)."""
+import dataclasses
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+from microfc_b200 import cases, pre_process  # noqa: E402
+from microfc_b200.simulation import Simulation  # noqa: E402
+from common import norm_linf, oracle_run  # noqa: E402
+
+CASES = {
+    "sod_1d": (lambda: cases.sod_1d(Nx=199), 40),
+    "shockbubble_2d": (lambda: cases.shockbubble_2d_cells(120, 64), 25),
+    "shearlayer_2d": (lambda: cases.shearlayer_2d(Nx=79, Ny=63), 25),          # periodic in x
+    "shockdroplet_2d": (lambda: cases.shockdroplet_2d(Nx=199, Ny=59), 20),      # reflective y
+    "shockbubble_3d": (lambda: cases.shockbubble_3d(nc=52), 6),
+}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def bcast(mine):
+        obj = [mine]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+
+    ok = True
+    for name in sys.argv[1:]:
+        mk, n = CASES[name]
+        cfg = cases.config(mk())
+        cfg = dataclasses.replace(cfg, t_step_stop=cfg.t_step_start + n)
+        cb = pre_process.generate_grid(cfg)
+        q0 = pre_process.generate_initial_condition(cfg, cb)
+        ref = None
+        if rank == 0:
+            ref, rows_ref = oracle_run(cfg, cb, q0)
+        for strict in (True, False):
+            sim = Simulation(cfg, cb, rank=rank, num_procs=world, strict=strict, device=local, broadcast_id=bcast)
+            sim.upload(sim.scatter(q0))
+            rows = sim.run()
+            mine = sim.download()
+            lay = sim.layout
+            sim.close()
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object((lay.interior_slices(), mine), parts, dst=0)
+            if rank == 0:
+                out = np.full_like(q0, np.nan)
+                for sl, blk in parts:
+                    out[(slice(None),) + sl] = blk
+                if strict:
+                    good = np.array_equal(out, ref)
+                    if cfg.run_time_info:
+                        good = good and all(a[2][0] == b[2][0] for a, b in zip(rows, rows_ref))
+                else:
+                    err = norm_linf(out, ref, cfg)
+                    good = bool((err <= 1e-10).all())
+                print(f"{name} world={world} strict={strict}: {'OK' if good else 'MISMATCH ' + str(norm_linf(out, ref, cfg))}", flush=True)
+                ok = ok and good
+    dist.barrier()
+    if rank == 0:
+        print("NCCL_WORKER_OK" if ok else "NCCL_WORKER_FAIL", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
