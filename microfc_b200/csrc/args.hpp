@@ -6,6 +6,11 @@
 
 namespace mfc {
 
+// CUtensorMap (128 opaque bytes, 64-byte aligned) without pulling <cuda.h> into device code
+struct alignas(64) TensorMap {
+    unsigned long long opaque[16];
+};
+
 struct SweepArgs {
     GridDesc g;
     const double *q;       // stage state, conservative (alpha_rho, mom, E, alpha), ghosts filled
@@ -30,6 +35,15 @@ struct SweepArgs {
     int variant;           // 2: TMA-ring kernels (k_xrow / k_march2), 1: v1 direct-load kernels
     int coef_uniform;      // 1: cuni[] holds the coefficients of every cell of this direction
     double cuni[kNumWenoCoef];   // uniform-grid WENO coefficients (COEF = 0 kernels)
+    // per-variable plane pointers (filled by the launcher from rhs / q1 / qout + v*fstride): the
+    // v2 kernels address a cell as plane pointer (constant bank) + 32-bit element offset, one
+    // IMAD.WIDE per access instead of 64-bit pointer arithmetic per variable
+    const double *q_v[kMaxE], *rhs_v[kMaxE], *q1_v[kMaxE];
+    double *rhsw_v[kMaxE], *qout_v[kMaxE];
+    // TMA descriptors (cuTensorMapEncodeTiled) of the stage state, the RHS accumulator and
+    // q_cons_ts(1) seen as 4-D tensors (x, y, z, variable): one cp.async.bulk.tensor copy
+    // brings a row of ALL variables into a ring slot, box = {kWX or kWY, 1, 1, E}
+    TensorMap tm_q, tm_rhs, tm_q1;
 };
 
 struct BcArgs {

@@ -76,6 +76,53 @@ __device__ __forceinline__ double sqrt_ratio_fast(double n, double d) {
     return n*y;
 }
 
+// 1/x with a cubically convergent correction: seed error e ~ 2^-23 -> e^3, i.e. ~1 ulp in 3 DFMAs
+__device__ __forceinline__ double rcp_fast3(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+// ------------------------------------------------------------------------------------------
+// WENO5-JS on a UNIFORM grid (fast build only).  On a uniform grid the coefficient arrays of
+// m_weno.fpp:223-347 reduce to the classical rationals
+//   poly_L = {1/3,-5/6 | -1/6,-1/3 | -2/3,1/6}   poly_R = {-1/6,2/3 | 1/3,1/6 | 5/6,-1/3}
+//   d_L = {1/10,3/5,3/10}   d_R = {3/10,3/5,1/10}
+//   beta = {4/3,-11/3,10/3 | 4/3,-5/3,4/3 | 10/3,-11/3,4/3}
+// (mfc_b200_init checks the computed tables against these to 1e-12 before selecting this
+// path).  The nonlinear weights only depend on RATIOS of d_k/beta_k^2, so beta is scaled by 3
+// and d by 10 (small integers: immediate operands), the weights 6 and 3 are folded into the
+// candidate increments, and the face value is formed as v_j + N/D so that rounding in the
+// weights only touches the (small) increment.  52 FP64 instructions per variable for both
+// faces instead of 66; results differ from the table form at the 1e-16 level.
+// eps3 = 3*weno_eps.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void weno5_uniform(const double v[5], double eps3, double &vL, double &vR) {
+    const double d1 = v[4] - v[3], d0 = v[3] - v[2], dm1 = v[2] - v[1], dm2 = v[1] - v[0];
+    const double p00 = d0*d0, pmm = dm1*dm1;
+    const double b0 = fma(d1, fma(4.0, d1, -11.0*d0), fma(10.0, p00, eps3));
+    const double b1 = fma(4.0, p00 + pmm, fma(-5.0*d0, dm1, eps3));
+    const double b2 = fma(dm2, fma(4.0, dm2, -11.0*dm1), fma(10.0, pmm, eps3));
+    const double q0 = b0*b0, q1 = b1*b1, q2 = b2*b2;
+    const double B0 = q1*q2, B1 = q0*q2, B2 = q0*q1;
+    const double DL = fma(6.0, B1, fma(3.0, B2, B0));          // 10*sum_k d_L(k) B_k
+    const double DR = fma(6.0, B1, fma(3.0, B0, B2));
+    const double m2 = -2.0*dm1, t2 = 2.0*d0;
+    const double eL0 = fma(1.0/3.0, d1, (-5.0/6.0)*d0);        // poly_L0 - v_j
+    const double eL1 = m2 - d0;                                // 6 (poly_L1 - v_j)
+    const double eL2 = fma(0.5, dm2, m2);                      // 3 (poly_L2 - v_j)
+    const double eR0 = fma(-0.5, d1, t2);                      // 3 (poly_R0 - v_j)
+    const double eR1 = t2 + dm1;                               // 6 (poly_R1 - v_j)
+    const double eR2 = fma(5.0/6.0, dm1, (-1.0/3.0)*dm2);      // poly_R2 - v_j
+    const double NL = fma(B0, eL0, fma(B1, eL1, B2*eL2));
+    const double NR = fma(B0, eR0, fma(B1, eR1, B2*eR2));
+    const double inv = rcp_fast3(DL*DR);
+    vL = fma(NL, DR*inv, v[2]);
+    vR = fma(NR, DL*inv, v[2]);
+}
+
 // ------------------------------------------------------------------------------------------
 // WENO5-JS on one 5-cell stencil v[0..4] = v(j-2..j+2), m_weno.fpp:476-531.
 // c[] = the 27 grid-dependent coefficients of cell j:
@@ -443,11 +490,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
         "MFC_DONE:\n"
         "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// one row of all E variables (box {W, 1, 1, E} of the 4-D tensor (x, y, z, variable)) -> smem
+__device__ __forceinline__ void tma_load_row(void *dst, const TensorMap *tm, int c0, int c1, int c2, unsigned long long *b) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(0), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_row(const TensorMap *tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(0) : "memory");
+}
 // generic-proxy accesses to a slot must be ordered before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kWX = 40;        // doubles staged per warp, row and variable by the x kernel (36 used)
-constexpr int kWY = 32;        // columns per warp in the y/z march
 // tuning knobs (tools/tune_variants.py builds and times alternatives)
 #ifndef MFC_RING_Y
 #define MFC_RING_Y 6
@@ -462,10 +516,17 @@ constexpr int kWY = 32;        // columns per warp in the y/z march
 constexpr int kRingY = MFC_RING_Y;   // row slots of the y/z march ring: 5 live rows + the rows in flight
 constexpr int kRingX = MFC_RING_X;   // row slots of the x kernel: 1 live row + the rows in flight
 constexpr int kWarpCells = 30; // cells finished per warp and row in the x kernel
+// doubles per ring slot: E rows of W doubles, padded so that every slot starts on a 128-byte line
+// (the TMA destination alignment)
+__host__ __device__ constexpr int slot_doubles(int E, int W) { return (E*W + 15)/16*16; }
 // Occupancy (measured at 512^3, profiles/r01_tune_occupancy.txt): x 5 CTAs x 4 warps (<= 96
 // registers, 40 KB of rings per CTA), y/z 4 CTAs x 4 warps (<= 128 registers, 6-slot rings,
 // 48 KB per CTA) is the fastest of the variants tried; 15 or 18 warps per SM with fewer
 // registers are slower.
+#ifndef MFC_MARCH_UNROLL
+#define MFC_MARCH_UNROLL 1
+#endif
+constexpr int kMarchUnroll = MFC_MARCH_UNROLL;   // unrolling the march renames the carried face state instead of copying it
 constexpr int kWarpsX = MFC_WARPS_X, kCtasX = MFC_CTAS_X;
 constexpr int kWarpsY = MFC_WARPS_Y, kCtasY = MFC_CTAS_Y;
 
@@ -506,21 +567,34 @@ __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, 
 #endif
 }
 
+// reconstruction of one variable at one cell: uniform-grid constants (COEF = 0, fast build only)
+// or the per-cell coefficient tables (m_weno.fpp:223-347)
 template <int COEF>
-__device__ __forceinline__ void get_coef(const SweepArgs &a, int cell, double c[27]) {
-    if (COEF == 0) {
-#pragma unroll
-        for (int i = 0; i < 27; i++) c[i] = a.cuni[i];
-    } else {
-        load_coef(a, cell, c);
+struct Weno {
+    static constexpr bool kUniform = COEF == 0 && !MFC_STRICT;
+    double c[kUniform ? 1 : 27];
+    double eps;
+    __device__ __forceinline__ void load(const SweepArgs &a, int cell) {
+        if (kUniform) {
+            eps = 3.0*a.eps;
+        } else {
+            load_coef(a, cell, c);
+            eps = a.eps;
+        }
     }
-}
+    __device__ __forceinline__ void operator()(const double s[5], double &vL, double &vR) const {
+        if (kUniform) weno5_uniform(s, eps, vL, vR);
+        else weno5(s, c, eps, vL, vR);
+    }
+};
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // operands of finish_cell2 that stream from HBM, fetched ahead of the Riemann solve.
 // ACC: the RHS of earlier directions is accumulated (m_rhs.fpp:610-620); RK: this is the last
 // direction, the TVD-RK statement a.rk_mode (1..4, or 0 = store the RHS) is fused in.
+// Cells are addressed as (per-variable plane pointer from the constant bank) + (32-bit element
+// offset within the plane): one IMAD.WIDE per access.
 //
 // Strict build: q_cons_ts(1) and the stage state are read back from HBM for the update.
 // Fast build: the stage state's momenta and energy are rebuilt from the primitive variables
@@ -531,90 +605,87 @@ struct CellIn {
     double r[ACC ? E : 1], q1[RK ? E : 1], qs[RK ? E : 1];
 };
 template <int NF, int ND, bool ACC, bool RK>
-__device__ __forceinline__ void load_cell(const SweepArgs &a, long long cell, CellIn<2*NF + ND + 1, ACC, RK> &in) {
+__device__ __forceinline__ void load_cell(const SweepArgs &a, unsigned off, CellIn<2*NF + ND + 1, ACC, RK> &in) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1;
-    const long long fs = a.g.fstride;
     if (ACC) {
-        const double *p = a.rhs + cell;
 #pragma unroll
-        for (int v = 0; v < E; v++) in.r[v] = __ldg(p + v*fs);
+        for (int v = 0; v < E; v++) in.r[v] = __ldg(a.rhs_v[v] + off);
     }
     if (RK) {
 #if MFC_STRICT
         if (a.rk_mode != 0) {
-            const double *p = a.q1 + cell;
 #pragma unroll
-            for (int v = 0; v < E; v++) in.q1[v] = __ldg(p + v*fs);
+            for (int v = 0; v < E; v++) in.q1[v] = __ldg(a.q1_v[v] + off);
         }
         if (a.rk_mode >= 2) {
-            const double *p = a.q + cell;
 #pragma unroll
-            for (int v = 0; v < ADV; v++) in.qs[v] = __ldg(p + v*fs);
+            for (int v = 0; v < ADV; v++) in.qs[v] = __ldg(a.q_v[v] + off);
         }
 #else
         if (a.rk_mode >= 2) {
-            const double *p = a.q1 + cell;
 #pragma unroll
-            for (int v = 0; v < E; v++) in.q1[v] = __ldg(p + v*fs);
+            for (int v = 0; v < E; v++) in.q1[v] = __ldg(a.q1_v[v] + off);
         }
 #endif
     }
 }
 template <int NF, int ND, bool ACC, bool RK>
-__device__ __forceinline__ void prefetch_cell(const SweepArgs &a, long long cell) {
+__device__ __forceinline__ void prefetch_cell(const SweepArgs &a, unsigned off) {
     constexpr int E = 2*NF + ND + 1;
-    const long long fs = a.g.fstride;
     if (ACC) {
-        const double *p = a.rhs + cell;
 #pragma unroll
-        for (int v = 0; v < E; v++) prefetch_l2(p + v*fs);
+        for (int v = 0; v < E; v++) prefetch_l2(a.rhs_v[v] + off);
     }
     if (RK) {
         if (a.rk_mode >= 2) {
-            const double *p = a.q1 + cell;
 #pragma unroll
-            for (int v = 0; v < E; v++) prefetch_l2(p + v*fs);
+            for (int v = 0; v < E; v++) prefetch_l2(a.q1_v[v] + off);
         }
     }
 }
 
 // RHS of one cell + fused RK stage.  pc = the cell's entry in the ring (stride LD between
 // variables: partial densities and volume fractions as stored, velocities and pressure in
-// place of momenta and energy); in = the operands fetched by load_cell.
+// place of momenta and energy); in = the operands fetched by load_cell; store = false masks
+// the stores (lanes beyond the domain, halo lanes of the x kernel).
 template <int NF, int ND, int LD, bool ACC, bool RK>
-__device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell, double rds, const double *pc,
+__device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, bool store, double rds, const double *pc,
                                              const CellIn<2*NF + ND + 1, ACC, RK> &in,
                                              const double *Fm, double ufm, const double *Fp, double ufp) {
     constexpr int E = 2*NF + ND + 1, MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
-    const long long fs = a.g.fstride;
     double x[E], al[NF];
 #pragma unroll
     for (int i = 0; i < NF; i++) al[i] = pc[(ADV + i)*LD];
-    const double du = rds*(ufp - ufm);
+#if MFC_STRICT
 #pragma unroll
     for (int v = 0; v < E; v++) {
         x[v] = rds*(Fm[v] - Fp[v]);
         if (ACC) x[v] = in.r[v] + x[v];
-        if (v >= ADV) {
-#if MFC_STRICT
-            x[v] = x[v] + rds*al[v - ADV]*(ufp - ufm);
+        if (v >= ADV) x[v] = x[v] + rds*al[v - ADV]*(ufp - ufm);
+    }
 #else
-            x[v] = fma(al[v - ADV], du, x[v]);
-#endif
-        }
-    }
-    if (!RK || a.rk_mode == 0) {
-        double *o = a.rhs + cell;
-#pragma unroll
-        for (int v = 0; v < E; v++) o[v*fs] = x[v];
-        return;
-    }
-    double *o = a.qout + cell;
-#if MFC_STRICT
+    const double du = rds*(ufp - ufm);
 #pragma unroll
     for (int v = 0; v < E; v++) {
-        const double qs = a.rk_mode >= 2 ? (v >= ADV ? al[v - ADV] : in.qs[v]) : 0.0;
-        o[v*fs] = rk_apply(a.rk_mode, in.q1[v], qs, x[v], a.dt);
+        const double dF = Fm[v] - Fp[v];
+        x[v] = ACC ? fma(rds, dF, in.r[v]) : rds*dF;
+        if (v >= ADV) x[v] = fma(al[v - ADV], du, x[v]);
+    }
+#endif
+    if (!RK || a.rk_mode == 0) {
+        if (store) {
+#pragma unroll
+            for (int v = 0; v < E; v++) a.rhsw_v[v][off] = x[v];
+        }
+        return;
+    }
+#if MFC_STRICT
+    if (store) {
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            const double qs = a.rk_mode >= 2 ? (v >= ADV ? al[v - ADV] : in.qs[v]) : 0.0;
+            a.qout_v[v][off] = rk_apply(a.rk_mode, in.q1[v], qs, x[v], a.dt);
+        }
     }
 #else
     // stage state rebuilt from the ring
@@ -635,14 +706,21 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell,
         v2 = fma(u, u, v2);
     }
     qs[EN] = fma(gamma, pc[EN*LD], pi_inf) + 5e-1*rho*v2;
-    // every TVD-RK statement is (c1 q1 + c2 qs + c3 dt rhs)*c4   (m_time_steppers.fpp:167,245,322,342)
+    // every TVD-RK statement is (c1 q1 + c2 qs + c3 dt rhs)*c4   (m_time_steppers.fpp:167,245,322,342),
+    // evaluated as k1 q1 + k2 qs + k3 rhs with the constants folded
     const int m = a.rk_mode;
-    const double c1 = m == 3 ? 3.0 : 1.0, c2 = m == 1 ? 0.0 : (m == 4 ? 2.0 : 1.0);
-    const double c3 = (m == 4 ? 2.0 : 1.0)*a.dt, c4 = m == 1 ? 1.0 : (m == 2 ? 0.5 : (m == 3 ? 0.25 : 1.0/3.0));
+    if (m == 1) {
+        if (store) {
 #pragma unroll
-    for (int v = 0; v < E; v++) {
-        const double q1 = m == 1 ? qs[v] : in.q1[v];
-        o[v*fs] = fma(c1, q1, fma(c2, qs[v], c3*x[v]))*c4;
+            for (int v = 0; v < E; v++) a.qout_v[v][off] = fma(a.dt, x[v], qs[v]);
+        }
+    } else {
+        const double c4 = m == 2 ? 0.5 : (m == 3 ? 0.25 : 1.0/3.0);
+        const double k1 = (m == 3 ? 3.0 : 1.0)*c4, k2 = (m == 4 ? 2.0 : 1.0)*c4, k3 = (m == 4 ? 2.0 : 1.0)*a.dt*c4;
+        if (store) {
+#pragma unroll
+            for (int v = 0; v < E; v++) a.qout_v[v][off] = fma(k1, in.q1[v], fma(k2, qs[v], k3*x[v]));
+        }
     }
 #endif
 }
@@ -657,7 +735,7 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, long long cell,
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int COEF, bool BC4>
 __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = E*kWX;
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = slot_doubles(E, kWX);
     constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridDesc &g = a.g;
@@ -669,20 +747,15 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
     const int k0 = blockIdx.y*a.rows, l = blockIdx.z;
     const int nrows = min(a.rows, g.N[1] + 1 - k0);
     const int x0 = jw - 4;                             // first staged column
-    const int nx = min(kWX, g.pitch - (x0 + kXoff));   // staged doubles per row (even)
-    const unsigned row_bytes = (unsigned)nx*8u;
-    const long long fs = g.fstride;
-    const long long base = g.at(x0, k0, l);
     if (lane == 0) {
         for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
+    // columns beyond the padded row are zero-filled by the TMA unit and count towards the bytes
     auto issue = [&](int r, int slot) {
-        mbar_expect_tx(&bar[slot], row_bytes*E);
-#pragma unroll
-        for (int v = 0; v < E; v++)
-            bulk_g2s(ring + slot*SLOT + v*kWX, a.q + v*fs + base + (long long)r*g.sy, row_bytes, &bar[slot]);
+        mbar_expect_tx(&bar[slot], (unsigned)(E*kWX*sizeof(double)));
+        tma_load_row(ring + slot*SLOT, &a.tm_q, x0 + kXoff, k0 + r + g.yoff, l + g.zoff, &bar[slot]);
     };
     if (lane == 0)
         for (int r = 0; r < min(R, nrows); r++) issue(r, r);
@@ -690,25 +763,26 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
     const int j_raw = jw - 1 + lane;
     const int j = min(j_raw, g.N[0] + 1);              // clamped lanes never store
     const int sx = j - x0;                             // staged index of my cell (3 .. 34)
-    double c[27];
-    get_coef<COEF>(a, j, c);
+    Weno<COEF> weno;
+    weno.load(a, j);
     const double rds = a.rds[j + g.b];
     const unsigned full = 0xffffffffu;
     const bool store_on = lane >= 1 && lane <= kWarpCells && j_raw <= g.N[0];
     const bool stab_on = a.stab_out != nullptr;
     double icfl = 0.0;
+    unsigned off = (unsigned)g.at(min(j, g.N[0]), k0, l);
+    const unsigned usy = (unsigned)g.sy;
 
     int slot = 0;
     unsigned phase = 0;
-    for (int r = 0; r < nrows; r++) {
+    for (int r = 0; r < nrows; r++, off += usy) {
         double *row = ring + slot*SLOT;
         mbar_wait(&bar[slot], phase);
-        if (lane < nx) prim_in_place<NF, ND, kWX>(row + lane, a.gammas, a.pi_infs);
-        if (lane + 32 < nx) prim_in_place<NF, ND, kWX>(row + lane + 32, a.gammas, a.pi_infs);
+        prim_in_place<NF, ND, kWX>(row + lane, a.gammas, a.pi_infs);
+        if (lane < kWX - 32) prim_in_place<NF, ND, kWX>(row + lane + 32, a.gammas, a.pi_infs);
         __syncwarp();
-        const long long cell = g.at(j, k0 + r, l);
         CellIn<E, ACC, RK> in;
-        if (store_on) load_cell<NF, ND, ACC, RK>(a, cell, in);
+        if (RK) load_cell<NF, ND, ACC, RK>(a, off, in);
         const double *p = row + sx;
         double vL[E], vR[E];
 #pragma unroll
@@ -716,13 +790,13 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
             double s[5];
 #pragma unroll
             for (int t = 0; t < 5; t++) s[t] = p[v*kWX + (t - 2)];
-            weno5(s, c, a.eps, vL[v], vR[v]);
+            weno(s, vL[v], vR[v]);
         }
         double pc[E];                                  // my cell's ring entry, kept for the finish
 #pragma unroll
         for (int v = 0; v < E; v++) pc[v] = (RK || v >= ADV || stab_on) ? p[v*kWX] : 0.0;
 #if !MFC_STRICT
-        if (stab_on && store_on) {                     // ICFL, m_data_output.fpp:215-233 (inviscid)
+        if (stab_on) {                                 // ICFL, m_data_output.fpp:215-233 (inviscid)
             double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
 #pragma unroll
             for (int i = 0; i < NF; i++) {
@@ -735,7 +809,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
             double m = (fabs(pc[NF]) + cs)*rds;
             if (ND >= 2) m = fmax(m, (fabs(pc[NF + (ND >= 2 ? 1 : 0)]) + cs)*__ldg(a.rds_t[0] + k0 + r + g.b));
             if (ND >= 3) m = fmax(m, (fabs(pc[NF + (ND >= 3 ? 2 : 0)]) + cs)*__ldg(a.rds_t[1] + l + g.b));
-            icfl = fmax(icfl, a.dt*m);
+            if (store_on) icfl = fmax(icfl, a.dt*m);
         }
 #endif
         fence_proxy_async();
@@ -761,7 +835,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 #pragma unroll
         for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
         ufm = __shfl_up_sync(full, uf, 1);
-        if (store_on) finish_cell2<NF, ND, 1, ACC, RK>(a, cell, rds, pc, in, Fm, ufm, F, uf);
+        finish_cell2<NF, ND, 1, ACC, RK>(a, off, store_on, rds, pc, in, Fm, ufm, F, uf);
     }
     if (stab_on) {                                     // all values >= 0: the bit pattern orders like the value
         unsigned long long b = (unsigned long long)__double_as_longlong(icfl);
@@ -774,106 +848,107 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 // ------------------------------------------------------------------------------------------
 // y / z sweep, v2.  Every WARP is an independent pipeline: it owns 32 consecutive x columns at
 // one transverse index and marches a pencil segment s0..s1 along the sweep direction.  Rows
-// s0-3 .. s1+3 stream through the warp's private 8-slot ring (5 live rows of the stencil + 3
-// rows in flight, one 256-byte bulk copy per variable and row); every lane converts, reads and
+// s0-3 .. s1+3 stream through the warp's private ring (5 live rows of the stencil + the rows
+// in flight, one 256-byte bulk copy per variable and row); every lane converts, reads and
 // reconstructs only its own column, carrying the previous cell's right-face state and the
 // previous face's flux in registers, so the only synchronisation is a __syncwarp before a slot
-// is handed back to the TMA engine.
+// is handed back to the TMA engine.  Lanes beyond the domain compute on whatever their ring
+// column holds and never store.
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int DIR, int COEF, bool BC4>
 __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, R = kRingY, SLOT = E*kWY;
+    constexpr int E = 2*NF + ND + 1, R = kRingY, SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
+    static_assert(R >= 6, "the ring holds the 5 live rows of the stencil plus at least one row in flight");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsY*R*SLOT) + warp*R;
-    const int j0 = (blockIdx.x*kWarpsY + warp)*kWY, j = j0 + lane;
+    const int j0 = (blockIdx.x*kWarpsY + warp)*kWY;
     if (j0 > g.N[0]) return;                           // whole warp out of range
+    const bool on = j0 + lane <= g.N[0];
     const int t = blockIdx.z;
     const int s0 = blockIdx.y*a.seg;
     const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
-    const bool on = j <= g.N[0];
     const long long ss = DIR == 1 ? g.sy : g.sz;
     const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the warp's columns
-    const int nx = min(kWY, g.pitch - (j0 + kXoff));
-    const unsigned row_bytes = (unsigned)nx*8u;
-    const long long fs = g.fstride;
     const int r_first = s0 - 3, r_last = s1 + 3;
     if (lane == 0) {
         for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
+    // tensor coordinates of row r of the warp's columns: (x, y, z) in the padded box
+    const int cx = j0 + kXoff, cy = (DIR == 1 ? 0 : t) + g.yoff, cz = (DIR == 1 ? t : 0) + g.zoff;
     auto issue = [&](int r, int slot) {
-        mbar_expect_tx(&bar[slot], row_bytes*E);
-#pragma unroll
-        for (int v = 0; v < E; v++)
-            bulk_g2s(ring + slot*SLOT + v*kWY, a.q + v*fs + base + (long long)r*ss, row_bytes, &bar[slot]);
+        mbar_expect_tx(&bar[slot], (unsigned)(E*kWY*sizeof(double)));
+        tma_load_row(ring + slot*SLOT, &a.tm_q, cx, DIR == 1 ? cy + r : cy, DIR == 1 ? cz : cz + r, &bar[slot]);
     };
     int next_issue = r_first + R;                      // only lane 0 issues, every lane counts
     if (lane == 0)
         for (int r = r_first; r < r_first + R && r <= r_last; r++) issue(r, r - r_first);
 
-    // ring bookkeeping (R need not be a power of two): slot of row s-2, and slot / phase of the
-    // next row to wait for and convert
-    int slot_lo = 0, conv = r_first, slot_cv = 0;
+    // ring bookkeeping (R need not be a power of two): slot / phase of the next row to wait for
+    // and convert, slot of row s-2 (the one handed back at the end of the iteration), and the
+    // lane's pointers to rows s-2 .. s+2
+    int slot_cv = 0, slot_lo = 0;
     unsigned phase_cv = 0;
+    auto convert_next = [&]() {
+        mbar_wait(&bar[slot_cv], phase_cv);
+        prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
+        if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
+    };
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) convert_next();        // rows s0-3 .. s0
+    const double *p0 = ring + lane, *p1 = p0 + SLOT, *p2 = p1 + SLOT, *p3 = p2 + SLOT, *p4 = p3 + SLOT;
+    const double *const ring_end = ring + R*SLOT;
+
     double vRp[E], Fp[E], ufp = 0.0;
 #pragma unroll
     for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
-    const long long col = base + lane;
+    const unsigned uss = (unsigned)ss;
+    // plane-relative element offset of cell s-1 of my column (lanes beyond the domain: column N)
+    unsigned off = (unsigned)(base + (min(j0 + lane, g.N[0]) - j0) + (long long)(s0 - 3)*ss);
+    Weno<COEF> weno;
+#pragma unroll kMarchUnroll
     for (int s = s0 - 1; s <= s1 + 1; s++) {
-        while (conv <= s + 2) {
-            mbar_wait(&bar[slot_cv], phase_cv);
-            if (on) prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
-            conv++;
-            if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
-        }
+        convert_next();                                // row s+2
+        off += uss;
         const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
-        const long long cellm = col + (long long)(s - 1)*ss;
-        if (on && s <= s1) prefetch_cell<NF, ND, ACC, RK>(a, cellm + ss);   // operands of the NEXT iteration's finish
-        if (on) {
-            double c[27];
-            get_coef<COEF>(a, s, c);
-            const double *p[5];
-#pragma unroll
-            for (int q = 0; q < 5; q++) {
-                const int sl = slot_lo + q;
-                p[q] = ring + (sl >= R ? sl - R : sl)*SLOT + lane;
-            }
-            double vL[E], vR[E];
-#pragma unroll
-            for (int v = 0; v < E; v++) {
-                double st[5];
-#pragma unroll
-                for (int q = 0; q < 5; q++) st[q] = p[q][v*kWY];
-                weno5(st, c, a.eps, vL[v], vR[v]);
-            }
-            if (s >= s0) {
-                CellIn<E, ACC, RK> in;
-                if (fin) load_cell<NF, ND, ACC, RK>(a, cellm, in);
-                if (BC4) {
-                    if (a.bc_beg == -4 && s == 0) {
-#pragma unroll
-                        for (int v = 0; v < E; v++) vRp[v] = vL[v];
-                    }
-                    if (a.bc_end == -4 && s == g.N[DIR] + 1) {
-#pragma unroll
-                        for (int v = 0; v < E; v++) vL[v] = vRp[v];
-                    }
-                }
-                double F[E], uf;
-                hllc<NF, ND, DIR>(vRp, vL, a.gammas, a.pi_infs, F, uf);
-                if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, cellm, a.rds[s - 1 + g.b], p[1], in, Fp, ufp, F, uf);   // p[1]: row s-1
-#pragma unroll
-                for (int v = 0; v < E; v++) Fp[v] = F[v];
-                ufp = uf;
-            }
-#pragma unroll
-            for (int v = 0; v < E; v++) vRp[v] = vR[v];
+        if (lane == 0 && s <= s1) {                    // operands of the NEXT iteration's finish -> L2
+            tma_prefetch_row(&a.tm_rhs, cx, DIR == 1 ? cy + s : cy, DIR == 1 ? cz : cz + s);
+            if (RK && a.rk_mode >= (MFC_STRICT ? 1 : 2)) tma_prefetch_row(&a.tm_q1, cx, DIR == 1 ? cy + s : cy, DIR == 1 ? cz : cz + s);
         }
+        weno.load(a, s);
+        double vL[E], vR[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) {
+            const double st[5] = {p0[v*kWY], p1[v*kWY], p2[v*kWY], p3[v*kWY], p4[v*kWY]};
+            weno(st, vL[v], vR[v]);
+        }
+        if (s >= s0) {
+            CellIn<E, ACC, RK> in;
+            if (fin) load_cell<NF, ND, ACC, RK>(a, off, in);
+            if (BC4) {
+                if (a.bc_beg == -4 && s == 0) {
+#pragma unroll
+                    for (int v = 0; v < E; v++) vRp[v] = vL[v];
+                }
+                if (a.bc_end == -4 && s == g.N[DIR] + 1) {
+#pragma unroll
+                    for (int v = 0; v < E; v++) vL[v] = vRp[v];
+                }
+            }
+            double F[E], uf;
+            hllc<NF, ND, DIR>(vRp, vL, a.gammas, a.pi_infs, F, uf);
+            if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, off, on, a.rds[s - 1 + g.b], p1, in, Fp, ufp, F, uf);   // p1: row s-1
+#pragma unroll
+            for (int v = 0; v < E; v++) Fp[v] = F[v];
+            ufp = uf;
+        }
+#pragma unroll
+        for (int v = 0; v < E; v++) vRp[v] = vR[v];
         fence_proxy_async();
         __syncwarp();                                  // row s-2 is dead for the whole warp
         if (next_issue <= r_last) {
@@ -881,6 +956,9 @@ __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_cons
             next_issue++;
         }
         if (++slot_lo == R) slot_lo = 0;
+        p0 = p1; p1 = p2; p2 = p3; p3 = p4;
+        p4 += SLOT;
+        if (p4 >= ring_end) p4 -= R*SLOT;
     }
 }
 

@@ -5,6 +5,7 @@
 //
 // There is NO CPU fallback: without a usable CUDA device every entry fails with
 // MFC_B200_ENODEVICE.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -69,6 +70,9 @@ struct Sim {
     int cur = 0;                       // which buffer holds q_cons_ts(1)
     const double *last_q = nullptr;    // state of the most recent RHS evaluation (what q_prim_vf reflects)
     double *prim = nullptr, *rhs = nullptr, *snap = nullptr;
+    // TMA descriptors of the three state buffers and the RHS accumulator, [0]: box kWX wide (x
+    // sweep), [1]: box kWY wide (y/z march)
+    TensorMap tm_state[3][2], tm_rhs[2];
     double *coef[3] = {nullptr, nullptr, nullptr};
     int clen[3] = {0, 0, 0}, coef_lo[3] = {0, 0, 0};
     int coef_uniform[3] = {0, 0, 0};   // every cell of the direction has the same 27 coefficients (to 1e-12)
@@ -155,6 +159,39 @@ void free_all() {
 }
 
 size_t field_bytes() { return (size_t)S.g.fstride*sizeof(double); }
+
+// E padded planes seen as the 4-D tensor (x, y, z, variable); box = one row of boxw columns of
+// every variable, which lands in shared memory as E consecutive runs of boxw doubles
+int make_tmap(TensorMap &out, double *base, int boxw) {
+    typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+            return fail(MFC_B200_ENODEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (Encode)fn;
+    }
+    const GridDesc &g = S.g;
+    const cuuint64_t dims[4] = {(cuuint64_t)g.pitch, (cuuint64_t)g.ey, (cuuint64_t)g.ez, (cuuint64_t)S.E};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.sy*8, (cuuint64_t)g.sz*8, (cuuint64_t)g.fstride*8};
+    const cuuint32_t box[4] = {(cuuint32_t)boxw, 1, 1, (cuuint32_t)S.E};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MFC_B200_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMap), "CUtensorMap is 128 bytes");
+    std::memcpy(&out, &m, sizeof(m));
+    return 0;
+}
+const TensorMap *state_tmap(const double *q, int which) {
+    for (int i = 0; i < 3; i++)
+        if (q == S.state[i]) return &S.tm_state[i][which];
+    return nullptr;
+}
 
 // ---- ghost cells: physical BCs (k_bc) and processor boundaries (pack / NCCL / unpack),
 // one direction after the other like m_rhs.fpp:686-908 ---------------------------------------
@@ -281,6 +318,11 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
+        {
+            const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
+            if (!tq || !t1) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
+            a.tm_q = *tq; a.tm_q1 = *t1; a.tm_rhs = S.tm_rhs[d == 0 ? 0 : 1];
+        }
         Scope sc(KC_SWEEP_X + d);
         const int n = S.L->sweep(S.nf, S.nd, d, a, S.st);
         if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
@@ -381,6 +423,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         S.variant = (e && e[0] == '1') ? 1 : 2;
     }
     S.g = make_grid(p->m, p->n, p->p, nd, S.b);
+    if (S.g.fstride >= (1LL << 32)) return fail(MFC_B200_EUNSUPPORTED, "more than 2^32 elements per field (kernels use 32-bit in-plane offsets)");
     for (int d = 0; d < 3; d++)
         for (int s = 0; s < 2; s++) {
             int c = p->bc[2*d + s];
@@ -393,6 +436,12 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     for (auto &s : S.state) { CK(cudaMalloc(&s, sb)); CK(cudaMemsetAsync(s, 0, sb, S.st)); }
     CK(cudaMalloc(&S.prim, field_bytes()*(nd + 1))); CK(cudaMemsetAsync(S.prim, 0, field_bytes()*(nd + 1), S.st));
     CK(cudaMalloc(&S.rhs, sb)); CK(cudaMemsetAsync(S.rhs, 0, sb, S.st));
+    for (int w = 0; w < 2; w++) {
+        int rc;
+        for (int i = 0; i < 3; i++)
+            if ((rc = make_tmap(S.tm_state[i][w], S.state[i], w == 0 ? kWX : kWY))) return rc;
+        if ((rc = make_tmap(S.tm_rhs[w], S.rhs, w == 0 ? kWX : kWY))) return rc;
+    }
     CK(cudaMalloc(&S.stab_dev, 3*sizeof(unsigned long long)));
     CK(cudaMallocHost(&S.stab_host, 3*sizeof(unsigned long long)));
     CK(cudaMallocHost(&S.stab_init, 3*sizeof(unsigned long long)));
@@ -400,15 +449,19 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         const int N = S.g.N[d], b = S.b;
         WenoTable t = build_weno5_table(p->cb[d], N, b);
         S.clen[d] = t.len; S.coef_lo[d] = t.lo; S.h_coef[d] = t.data;
-        {   // uniform grid?  then the per-cell coefficients agree to rounding and the fast
-            // kernels take them (those of the middle cell) as constants
-            const int mid = t.len/2;
+        {   // uniform grid?  then every cell's coefficients equal the classical WENO5-JS rationals
+            // to rounding, and the fast kernels use those as compile-time constants
+            // (weno5_uniform in kernels.cuh); otherwise they read the per-cell tables
+            static const double classic[kNumWenoCoef] = {
+                1.0/3, -5.0/6, -1.0/6, -1.0/3, -2.0/3, 1.0/6,            // poly_coef_cbL
+                -1.0/6, 2.0/3, 1.0/3, 1.0/6, 5.0/6, -1.0/3,              // poly_coef_cbR
+                0.1, 0.6, 0.3, 0.3, 0.6, 0.1,                            // d_cbL, d_cbR
+                4.0/3, -11.0/3, 10.0/3, 4.0/3, -5.0/3, 4.0/3, 10.0/3, -11.0/3, 4.0/3};   // beta_coef
             bool uni = true;
             for (int c = 0; c < kNumWenoCoef; c++) {
-                const double ref = t.data[(size_t)c*t.len + mid];
-                S.cuni[d][c] = ref;
+                S.cuni[d][c] = classic[c];
                 for (int i = 0; i < t.len && uni; i++)
-                    if (std::fabs(t.data[(size_t)c*t.len + i] - ref) > 1e-12*std::fabs(ref) + 1e-300) uni = false;
+                    if (std::fabs(t.data[(size_t)c*t.len + i] - classic[c]) > 1e-12) uni = false;
             }
             S.coef_uniform[d] = uni ? 1 : 0;
         }

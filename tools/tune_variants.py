@@ -13,17 +13,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    # name: (RING_Y, WARPS_Y, CTAS_Y, RING_X, WARPS_X, CTAS_X)
-    "y8w4c3_x4w4c4": (8, 4, 3, 4, 4, 4),
-    "y6w4c4_x4w4c5": (6, 4, 4, 4, 4, 5),
-    "y7w5c3_x3w4c6": (7, 5, 3, 3, 4, 6),
-    "y6w6c3_x4w6c3": (6, 6, 3, 4, 6, 3),
+    # name: (RING_Y, WARPS_Y, CTAS_Y, RING_X, WARPS_X, CTAS_X, extra -D flags)
+    "y6w4c4_x4w4c5_u2": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_UNROLL=2"),
+    "y6w4c4_x4w4c5_u1": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_UNROLL=1"),
+    "y8w4c3_x4w4c4_u1": (8, 4, 3, 4, 4, 4, "-DMFC_MARCH_UNROLL=1"),
+    "y8w4c3_x4w4c4_u2": (8, 4, 3, 4, 4, 4, "-DMFC_MARCH_UNROLL=2"),
 }
 
 
 def defs(v):
-    ry, wy, cy, rx, wx, cx = v
-    return f"-DMFC_RING_Y={ry} -DMFC_WARPS_Y={wy} -DMFC_CTAS_Y={cy} -DMFC_RING_X={rx} -DMFC_WARPS_X={wx} -DMFC_CTAS_X={cx}"
+    ry, wy, cy, rx, wx, cx, extra = v
+    return f"-DMFC_RING_Y={ry} -DMFC_WARPS_Y={wy} -DMFC_CTAS_Y={cy} -DMFC_RING_X={rx} -DMFC_WARPS_X={wx} -DMFC_CTAS_X={cx} {extra}"
 
 
 def build_one(name):
