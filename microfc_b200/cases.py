@@ -155,10 +155,12 @@ def shockbubble_2d_cells(ncx: int, ncy: int, Nt: int = 100) -> Dict:
     return d
 
 
-def shockdroplet_2d(Nx: float = 5000., Ny: float = 740., Nt: int = 10, viscous: bool = False) -> Dict:
+def shockdroplet_2d(Nx: float = 5000., Ny: float = 740., Nt: int = 10, viscous: bool = False, Re: float = 100.0) -> Dict:
     """examples/2D_shockdroplet/case.py (water droplet in air, bc_y%beg = -2 symmetry);
-    viscous=True enables fluid_pp(i)%Re(1:2) as examples/2D_viscous/case.py:91-94 does
-    (BASELINE config 4)."""
+    viscous=True sets fluid_pp(i)%Re(1:2) for both fluids the way examples/2D_viscous/case.py:91-94
+    does (BASELINE config 4).  The VALUE used there (1e-4, i.e. a viscosity of 1e4) is only stable
+    at that case's dt = 5e-10; at this case's dt = 0.1 dx/c the scheme -- the CPU oracle included --
+    blows up within two steps, so the default here is Re = 100 (viscous CFL ~ 5e-4)."""
     ps = 664016.5
     rho_post_a, rho_w = 3.757918216, 1000
     gam_a, gam_w, pi_w = 1.4, 6.12, 3.43E8
@@ -195,8 +197,8 @@ def shockdroplet_2d(Nx: float = 5000., Ny: float = 740., Nt: int = 10, viscous: 
     }
     if viscous:
         for i in (1, 2):
-            d[f'fluid_pp({i})%Re(1)'] = 0.0001
-            d[f'fluid_pp({i})%Re(2)'] = 0.0001
+            d[f'fluid_pp({i})%Re(1)'] = Re
+            d[f'fluid_pp({i})%Re(2)'] = Re
     return d
 
 

@@ -44,6 +44,38 @@ struct SweepArgs {
     // q_cons_ts(1) seen as 4-D tensors (x, y, z, variable): one cp.async.bulk.tensor copy
     // brings a row of ALL variables into a ring slot, box = {kWX or kWY, 1, 1, E}
     TensorMap tm_q, tm_rhs, tm_q1;
+    // viscous runs only (else nullptr): the sweep stores vel_src (nd planes) and Re_avg (2 planes)
+    // of every face it solves, for k_visc (m_riemann_solvers.fpp:225-230,314-324)
+    double *visc_face;
+    double Res[2][kMaxFluids];
+    int Re_idx[2][kMaxFluids], Re_size[2];
+};
+
+// viscous source flux + its RHS contribution for one direction (m_riemann_solvers.fpp:683-902,
+// m_rhs.fpp:591-604,639-652), and the velocity gradients of the weno_Re_flux branch
+struct ViscArgs {
+    GridDesc g;
+    const double *prim;        // velocity (nd planes) + pressure
+    const double *visc_face;   // vel_src (nd) + Re_avg (2) per face of direction dir
+    double *grad;              // dq_prim_d{x,y}_qp: nd*nd planes, [dd*nd + v] (weno_Re_flux only)
+    double *rhs;
+    const double *coef[3];     // WENO coefficient tables per direction
+    int clen[3], coef_lo[3];
+    const double *cc[3];       // cell centres s_cc(-b:N+b)
+    const double *ds[3];       // cell widths  ds(-b:N+b)
+    double eps;
+    int dir, nf, weno_Re_flux;
+    int bc_beg, bc_end;
+    int Re_size[2];
+};
+
+// the TVD-RK statement as a separate pass (viscous runs, where it cannot be fused into the sweep)
+struct RkArgs {
+    GridDesc g;
+    const double *q1, *qs, *rhs;
+    double *qout;
+    double dt;
+    int rk_mode, E;
 };
 
 struct BcArgs {
@@ -96,6 +128,9 @@ struct Launchers {
     int (*halo_pack)(const HaloArgs &, cudaStream_t);
     int (*halo_unpack)(const HaloArgs &, cudaStream_t);
     int (*stability)(int nf, int nd, const StabArgs &, cudaStream_t);
+    int (*visc_grad)(int nd, const ViscArgs &, cudaStream_t);
+    int (*visc)(int nd, const ViscArgs &, cudaStream_t);
+    int (*rk)(const RkArgs &, cudaStream_t);
 };
 const Launchers &launchers_fast();
 const Launchers &launchers_strict();

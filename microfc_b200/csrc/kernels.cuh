@@ -182,10 +182,11 @@ __device__ __forceinline__ void weno5(const double v[5], const double c[27], dou
 // sweep direction (dir_idx(1), :464-470).  dir_flg is folded in exactly: it is 0 or 1, and
 // 1*x + 0*y == x for finite y.
 //   F[E]  : flux_rs*_vf          uf : vel_src_rs*_vf(normal) = flux_src_rs*_vf(advxb) (:325)
+//   vs[ND]: vel_src_rs*_vf of every direction (:314-324), consumed by the viscous source flux
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int NRM>
 __device__ __forceinline__ void hllc(const double *L, const double *R, const double *gam, const double *pinf,
-                                     double *F, double &uf) {
+                                     double *F, double &uf, double *vs) {
     constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
 #if !MFC_STRICT
     // Fast build: the same solver with three exact-arithmetic identities applied.
@@ -241,6 +242,8 @@ __device__ __forceinline__ void hllc(const double *L, const double *R, const dou
     }
     F[EN] = fma(u, E_K + pres, s_MP*(fma(xi, fma(s_S - u, fma(rho, s_S, p_over), E_K), -E_K)));
     uf = w;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vs[i] = i == NRM ? w : (left ? L[MOM + i] : R[MOM + i]);
 #else
     double vel_L_rms = 0.0, vel_R_rms = 0.0;                            // :138-145
 #pragma unroll
@@ -295,7 +298,41 @@ __device__ __forceinline__ void hllc(const double *L, const double *R, const dou
     for (int i = 0; i < NF; i++)                                        // :304-310
         F[ADV + i] = xi_M*L[ADV + i]*(uL + s_M*(xi_L - 1.0)) + xi_P*R[ADV + i]*(uR + s_P*(xi_R - 1.0));
     uf = xi_M*(uL + s_M*(xi_L - 1.0)) + xi_P*(uR + s_P*(xi_R - 1.0));   // :316-325
+#pragma unroll
+    for (int i = 0; i < ND; i++) vs[i] = i == NRM ? uf : xi_M*L[MOM + i] + xi_P*R[MOM + i];
 #endif
+}
+
+// Face Reynolds numbers for the viscous source flux, m_riemann_solvers.fpp:169-200,225-230:
+// Re_K(i) = 1/max(sum_q alpha_K(Re_idx(i,q))/Res(i,q), sgm_eps), Re_avg = 2/(1/Re_L + 1/Re_R).
+template <int NF, int ND>
+__device__ __forceinline__ void face_reynolds(const double *L, const double *R, const SweepArgs &a, double Re_avg[2]) {
+    constexpr int ADV = NF + ND + 1;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double rl = a.Re_size[i] > 0 ? 0.0 : -1e6, rr = rl;
+        for (int q = 0; q < a.Re_size[i]; q++) {
+            double al = L[ADV], ar = R[ADV];
+#pragma unroll
+            for (int f = 1; f < NF; f++)
+                if (a.Re_idx[i][q] == f) { al = L[ADV + f]; ar = R[ADV + f]; }
+            rl = al/a.Res[i][q] + rl;
+            rr = ar/a.Res[i][q] + rr;
+        }
+        const double Re_L = 1.0/fmax(rl, 1e-16), Re_R = 1.0/fmax(rr, 1e-16);
+        Re_avg[i] = 2.0/(1.0/Re_L + 1.0/Re_R);
+    }
+}
+// vel_src (ND planes) and Re_avg (2 planes) of the face whose LEFT cell has in-plane offset off
+template <int NF, int ND>
+__device__ __forceinline__ void store_visc_face(const SweepArgs &a, unsigned off, const double *L, const double *R, const double *vs) {
+    double Re_avg[2];
+    face_reynolds<NF, ND>(L, R, a, Re_avg);
+    const long long fs = a.g.fstride;
+#pragma unroll
+    for (int i = 0; i < ND; i++) a.visc_face[i*fs + off] = vs[i];
+    a.visc_face[ND*fs + off] = Re_avg[0];
+    a.visc_face[(ND + 1)*fs + off] = Re_avg[1];
 }
 
 // pointer to reconstruction variable v of the stage state: partial densities and volume
@@ -387,7 +424,8 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ SweepAr
             for (int v = 0; v < E; v++) Rs[v] = Ls[v];
         }
         double F[E], uf;
-        hllc<NF, ND, 0>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+        double vs[ND];
+        hllc<NF, ND, 0>(Ls, Rs, a.gammas, a.pi_infs, F, uf, vs);
         double Fm[E], ufm;
 #pragma unroll
         for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
@@ -446,7 +484,8 @@ __global__ void __launch_bounds__(128) k_sweep_march(const __grid_constant__ Swe
                 for (int v = 0; v < E; v++) Rs[v] = Ls[v];
             }
             double F[E], uf;
-            hllc<NF, ND, DIR>(Ls, Rs, a.gammas, a.pi_infs, F, uf);
+            double vs[ND];
+            hllc<NF, ND, DIR>(Ls, Rs, a.gammas, a.pi_infs, F, uf, vs);
             if (s >= s0 + 1)
                 finish_cell<NF, ND>(a, cell - ss, a.rds[s - 1 + g.b], Fp, ufp, F, uf);
 #pragma unroll
@@ -830,7 +869,10 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
             }
         }
         double F[E], uf;
-        hllc<NF, ND, 0>(vR, Rs, a.gammas, a.pi_infs, F, uf);
+        double vs[ND];
+        hllc<NF, ND, 0>(vR, Rs, a.gammas, a.pi_infs, F, uf, vs);
+        if (a.visc_face != nullptr && lane <= kWarpCells && j_raw <= g.N[0])   // faces -1/2 .. N+1/2, keyed by the left cell
+            store_visc_face<NF, ND>(a, off, vR, Rs, vs);
         double Fm[E], ufm;
 #pragma unroll
         for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
@@ -941,7 +983,9 @@ __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_cons
                 }
             }
             double F[E], uf;
-            hllc<NF, ND, DIR>(vRp, vL, a.gammas, a.pi_infs, F, uf);
+            double vs[ND];
+            hllc<NF, ND, DIR>(vRp, vL, a.gammas, a.pi_infs, F, uf, vs);
+            if (a.visc_face != nullptr && on) store_visc_face<NF, ND>(a, off, vRp, vL, vs);   // face s-1/2, left cell s-1
             if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, off, on, a.rds[s - 1 + g.b], p1, in, Fp, ufp, F, uf);   // p1: row s-1
 #pragma unroll
             for (int v = 0; v < E; v++) Fp[v] = F[v];
@@ -1131,6 +1175,169 @@ __global__ void __launch_bounds__(256) k_stability(const __grid_constant__ StabA
     if ((threadIdx.x & 31) == 0) {
         atomicMax(a.out + 0, bi);
         if (visc) { atomicMax(a.out + 1, bv); atomicMin(a.out + 2, br); }
+    }
+}
+
+// ==========================================================================================
+// Viscous path (any fluid_pp(i)%Re > 0; 1-D / 2-D like the reference).  Correctness-first
+// kernels beside the fused sweeps: the sweeps store vel_src and Re_avg of every face they solve
+// (store_visc_face); k_visc turns them and the velocity gradients into the viscous source flux
+// of the cell's two faces and adds its divergence to the RHS, in the reference's order
+// (direction by direction, after the inviscid terms of that direction).
+// ==========================================================================================
+__device__ __forceinline__ void weno_at(const double *f, long long cell, long long stride, const double *coef, int clen,
+                                        int coef_lo, int idx, double eps, double &vL, double &vR) {
+    double c[27], st[5];
+    const double *p = coef + (idx - coef_lo);
+#pragma unroll
+    for (int i = 0; i < 27; i++) c[i] = p[(long long)i*clen];
+#pragma unroll
+    for (int q = 0; q < 5; q++) st[q] = f[cell + (long long)(q - 2)*stride];
+    weno5(st, c, eps, vL, vR);
+}
+
+// weno_Re_flux branch, m_viscous.fpp:186-217: velocities are WENO-reconstructed along every
+// direction i and the divergence theorem gives the cell gradient
+//   dq_prim_d<i>_qp(v) = 1/ds_i (vR - vL)                              (:417-422, :444-449)
+// over cells -4 .. N+4 of every active direction (what the later reconstruction reads).
+template <int ND>
+__global__ void __launch_bounds__(128) k_visc_grad(const __grid_constant__ ViscArgs a) {
+    const GridDesc &g = a.g;
+    const int j = (int)(blockIdx.x*blockDim.x + threadIdx.x) - 4;
+    const int k = ND > 1 ? (int)blockIdx.y - 4 : 0;
+    if (j > g.N[0] + 4) return;
+    const int c[3] = {j, k, 0};
+    const long long cell = g.at(j, k, 0), fs = g.fstride;
+#pragma unroll
+    for (int i = 0; i < ND; i++)
+#pragma unroll
+        for (int v = 0; v < ND; v++) {
+            double vL, vR;
+            weno_at(a.prim + v*fs, cell, g.stride(i), a.coef[i], a.clen[i], a.coef_lo[i], c[i], a.eps, vL, vR);
+            a.grad[(i*ND + v)*fs + cell] = 1.0/a.ds[i][c[i] + g.b]*(vR - vL);
+        }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a) {
+    const GridDesc &g = a.g;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (j > g.N[0]) return;
+    const int id = a.dir, b = g.b;
+    const int c[3] = {j, k, 0};
+    const long long cell = g.at(j, k, 0), fs = g.fstride, sid = g.stride(id);
+    const int MOM = a.nf, EN = a.nf + ND;
+    double fm[2][ND], fe[2];                       // flux_src(mom), flux_src(E) of faces c-1/2 and c+1/2
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int f = c[id] - 1 + side;            // the face's left cell along id
+        const long long cl = cell + (long long)(side - 1)*sid, cr = cl + sid;
+        double vsrc[ND], Re_avg[2];
+#pragma unroll
+        for (int i = 0; i < ND; i++) vsrc[i] = a.visc_face[i*fs + cl];
+        Re_avg[0] = a.visc_face[ND*fs + cl];
+        Re_avg[1] = a.visc_face[(ND + 1)*fs + cl];
+        // avg[dd][v] = 5d-1*(dvelL_d<dd>(v)(j,k) + dvelR_d<dd>(v)(j+1,k)), m_riemann_solvers.fpp:716-899
+        double avg[ND][ND];
+#pragma unroll
+        for (int dd = 0; dd < ND; dd++)
+#pragma unroll
+            for (int v = 0; v < ND; v++) {
+                double dR, dL;                     // dqR(left cell), dqL(right cell)
+                if (a.weno_Re_flux) {              // m_rhs.fpp:513-529: gradients reconstructed along id
+                    const double *G = a.grad + (dd*ND + v)*fs;
+                    double vLl, vRl, vLr, vRr;
+                    weno_at(G, cl, sid, a.coef[id], a.clen[id], a.coef_lo[id], f, a.eps, vLl, vRl);
+                    weno_at(G, cr, sid, a.coef[id], a.clen[id], a.coef_lo[id], f + 1, a.eps, vLr, vRr);
+                    dR = vRl; dL = vLr;
+                    if (a.bc_beg == -4 && f == -1) dR = dL;          // m_riemann_solvers.fpp:489-511
+                    if (a.bc_end == -4 && f == g.N[id]) dL = dR;     // :525-548
+                } else {                           // m_viscous.fpp:219-347: finite differences
+                    const double *u = a.prim + v*fs;
+                    if (dd == id) {
+                        const double *cc = a.cc[id] + b;
+                        dR = (u[cr] - u[cl])/(cc[f + 1] - cc[f]);    // dqR(c) :237-248 == dqL(c+1) :224-235
+                        dL = dR;
+                    } else {
+                        const long long sd = g.stride(dd);
+                        const double *cc = a.cc[dd] + b;
+                        const int t = c[dd];
+                        const double sLr = (u[cr] - u[cr - sd])/(cc[t] - cc[t - 1]), sRr = (u[cr + sd] - u[cr])/(cc[t + 1] - cc[t]);
+                        const double sLl = (u[cl] - u[cl - sd])/(cc[t] - cc[t - 1]), sRl = (u[cl + sd] - u[cl])/(cc[t + 1] - cc[t]);
+                        dR = 25e-2*(sLr + sRr + sLl + sRl);          // :300-307 at the left cell == :283-290 at the right cell
+                        dL = dR;
+                    }
+                }
+                avg[dd][v] = 5e-1*(dR + dL);
+            }
+        double m[ND], e = 0.0;                     // s_initialize_riemann_solver zeroes flux_src, :627-670
+#pragma unroll
+        for (int i = 0; i < ND; i++) m[i] = 0.0;
+        if (id == 0) {
+            if (a.Re_size[0] > 0) {                // :714-736
+                const double tau = (4.0/3.0)*avg[0][0]/Re_avg[0];
+                m[0] = m[0] - tau; e = e - vsrc[0]*tau;
+            }
+            if (a.Re_size[1] > 0) {                // :738-760
+                const double tau = avg[0][0]/Re_avg[1];
+                m[0] = m[0] - tau; e = e - vsrc[0]*tau;
+            }
+            if (ND > 1) {
+                if (a.Re_size[0] > 0) {            // :764-801
+                    double tau[2];
+                    tau[0] = -(2.0/3.0)*avg[ND > 1 ? 1 : 0][ND > 1 ? 1 : 0]/Re_avg[0];
+                    tau[1] = (avg[ND > 1 ? 1 : 0][0] + avg[0][ND > 1 ? 1 : 0])/Re_avg[0];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        m[ND > 1 ? i : 0] = m[ND > 1 ? i : 0] - tau[i];
+                        e = e - vsrc[ND > 1 ? i : 0]*tau[i];
+                    }
+                }
+                if (a.Re_size[1] > 0) {            // :803-825
+                    const double tau = avg[ND > 1 ? 1 : 0][ND > 1 ? 1 : 0]/Re_avg[1];
+                    m[0] = m[0] - tau; e = e - vsrc[0]*tau;
+                }
+            }
+        } else if (ND > 1) {
+            constexpr int Y = ND > 1 ? 1 : 0;
+            if (a.Re_size[0] > 0) {                // :831-872
+                double tau[2];
+                tau[0] = (avg[Y][0] + avg[0][Y])/Re_avg[0];
+                tau[1] = (4.0*avg[Y][Y] - 2.0*avg[0][0])/(3.0*Re_avg[0]);
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    m[ND > 1 ? i : 0] = m[ND > 1 ? i : 0] - tau[i];
+                    e = e - vsrc[ND > 1 ? i : 0]*tau[i];
+                }
+            }
+            if (a.Re_size[1] > 0) {                // :874-899
+                const double tau = (avg[0][0] + avg[Y][Y])/Re_avg[1];
+                m[Y] = m[Y] - tau; e = e - vsrc[Y]*tau;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ND; i++) fm[side][i] = m[i];
+        fe[side] = e;
+    }
+    const double dsj = a.ds[id][c[id] + b];        // m_rhs.fpp:591-604, :639-652
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        double *r = a.rhs + (MOM + i)*fs + cell;
+        *r = *r + 1.0/dsj*(fm[0][i] - fm[1][i]);
+    }
+    double *r = a.rhs + EN*fs + cell;
+    *r = *r + 1.0/dsj*(fe[0] - fe[1]);
+}
+
+// the TVD-RK statement on its own (m_time_steppers.fpp:167,245,322,342), interior cells only
+__global__ void __launch_bounds__(256) k_rk(const __grid_constant__ RkArgs a) {
+    const GridDesc &g = a.g;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j > g.N[0]) return;
+    const long long cell = g.at(j, blockIdx.y, blockIdx.z), fs = g.fstride;
+    for (int v = 0; v < a.E; v++) {
+        const long long o = v*fs + cell;
+        a.qout[o] = rk_apply(a.rk_mode, a.q1[o], a.qs[o], a.rhs[o], a.dt);
     }
 }
 

@@ -25,9 +25,9 @@ using namespace mfc;
 
 namespace {
 
-enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_COUNT };
+enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_RK, KC_COUNT };
 const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_sweep_x", "k_sweep_march<y>", "k_sweep_march<z>",
-                                      "k_stability", "k_halo_pack", "k_halo_unpack"};
+                                      "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_rk"};
 
 // NCCL is resolved at run time so the library loads (and every symbol is exported) on hosts
 // without it; only mfc_b200_comm_init needs it.  In a process that already imported torch
@@ -78,7 +78,11 @@ struct Sim {
     int coef_uniform[3] = {0, 0, 0};   // every cell of the direction has the same 27 coefficients (to 1e-12)
     double cuni[3][kNumWenoCoef];
     int variant = 2;                   // sweep kernel generation (MFC_B200_KERNELS=1 selects the v1 kernels)
-    double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr};
+    double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr}, *cc[3] = {nullptr, nullptr, nullptr};
+    // viscous runs: vel_src + Re_avg per face (nd+2 planes), dq_prim_d (nd*nd planes, weno_Re_flux)
+    double *visc_face = nullptr, *visc_grad = nullptr;
+    double Res[2][kMaxFluids];
+    int Re_idx[2][kMaxFluids], Re_size[2] = {0, 0};
     std::vector<double> h_coef[3];
     unsigned long long *stab_dev = nullptr, *stab_host = nullptr, *stab_init = nullptr;
     bool stab_pending = false;
@@ -139,9 +143,9 @@ void prof_collect() {
 void free_all() {
     auto fr = [](double *&p) { if (p) cudaFree(p); p = nullptr; };
     for (auto &s : S.state) fr(s);
-    fr(S.prim); fr(S.rhs); fr(S.snap);
+    fr(S.prim); fr(S.rhs); fr(S.snap); fr(S.visc_face); fr(S.visc_grad);
     for (int d = 0; d < 3; d++) {
-        fr(S.coef[d]); fr(S.rds[d]); fr(S.ds[d]);
+        fr(S.coef[d]); fr(S.rds[d]); fr(S.ds[d]); fr(S.cc[d]);
         for (int s = 0; s < 2; s++) { fr(S.sendbuf[d][s]); fr(S.recvbuf[d][s]); }
     }
     if (S.stab_dev) { cudaFree(S.stab_dev); S.stab_dev = nullptr; }
@@ -269,7 +273,10 @@ int run_stability(const double *q, double dt) {
     a.g = S.g; a.q = q; a.prim = S.prim; a.dt = dt; a.out = S.stab_dev;
     for (int d = 0; d < 3; d++) a.ds[d] = S.ds[d];
     for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
-    a.Re_size[0] = a.Re_size[1] = 0;
+    for (int i = 0; i < 2; i++) {
+        a.Re_size[i] = S.Re_size[i];
+        for (int q = 0; q < kMaxFluids; q++) { a.Res[i][q] = S.Res[i][q]; a.Re_idx[i][q] = S.Re_idx[i][q]; }
+    }
     {
         Scope sc(KC_STAB); sc.done(S.L->stability(S.nf, S.nd, a, S.st));
     }
@@ -296,7 +303,8 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     if (stop && S.p.run_time_info && want_stab && S.last_q)
         if ((rc = run_stability(S.last_q, dt))) return rc;
     if ((rc = fill_ghosts(q))) return rc;                    // m_rhs.fpp:435
-    if (S.variant != 2 && (rc = run_prim(q))) return rc;     // :445-447 (v2: fused into the sweeps)
+    // :445-447 (v2: fused into the sweeps; the viscous kernels read the velocity planes)
+    if ((S.variant != 2 || S.viscous) && (rc = run_prim(q))) return rc;
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
     S.last_q = q;
     // m_time_steppers.fpp:288-290.  Inviscid fast build: the ICFL maximum is taken by the x sweep
@@ -305,6 +313,14 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     const bool fuse_stab = do_stab && S.variant == 2 && !S.p.strict_math && !S.viscous;
     if (do_stab && !fuse_stab && (rc = run_stability(q, dt))) return rc;
     if (fuse_stab && (rc = stab_reset())) return rc;
+    ViscArgs va{};
+    if (S.viscous) {                                         // :456-464 s_get_viscous
+        va.g = S.g; va.prim = S.prim; va.visc_face = S.visc_face; va.grad = S.visc_grad; va.rhs = S.rhs;
+        for (int d = 0; d < 3; d++) { va.coef[d] = S.coef[d]; va.clen[d] = S.clen[d]; va.coef_lo[d] = S.coef_lo[d]; va.cc[d] = S.cc[d]; va.ds[d] = S.ds[d]; }
+        va.eps = S.p.weno_eps; va.nf = S.nf; va.weno_Re_flux = S.p.weno_Re_flux;
+        va.Re_size[0] = S.Re_size[0]; va.Re_size[1] = S.Re_size[1];
+        if (S.p.weno_Re_flux) { Scope sc(KC_VISC); sc.done(S.L->visc_grad(S.nd, va, S.st)); }
+    }
     for (int d = 0; d < S.nd; d++) {                         // :469
         SweepArgs a{};
         a.g = S.g; a.q = q; a.prim = S.prim; a.rhs = S.rhs; a.q1 = q1; a.qout = qout;
@@ -313,7 +329,12 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
         a.bc_beg = S.p.bc[2*d]; a.bc_end = S.p.bc[2*d + 1];
         a.first_dir = d == 0;
-        a.rk_mode = d == S.nd - 1 ? rk_mode : 0;
+        a.rk_mode = (d == S.nd - 1 && !S.viscous) ? rk_mode : 0;
+        a.visc_face = S.viscous ? S.visc_face : nullptr;
+        for (int i = 0; i < 2; i++) {
+            a.Re_size[i] = S.Re_size[i];
+            for (int k = 0; k < kMaxFluids; k++) { a.Res[i][k] = S.Res[i][k]; a.Re_idx[i][k] = S.Re_idx[i][k]; }
+        }
         a.variant = S.variant; a.coef_uniform = S.coef_uniform[d];
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
@@ -328,6 +349,14 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
         sc.done(n);
         if (fuse_stab && d == 0 && (rc = stab_reduce_and_copy())) return rc;
+        if (S.viscous) {                                     // m_rhs.fpp:591-604, :639-652
+            va.dir = d; va.bc_beg = S.p.bc[2*d]; va.bc_end = S.p.bc[2*d + 1];
+            Scope sv(KC_VISC); sv.done(S.L->visc(S.nd, va, S.st));
+        }
+    }
+    if (S.viscous && rk_mode != 0) {                         // the RK statement cannot be fused into the last sweep
+        RkArgs r{S.g, q1, q, S.rhs, qout, dt, rk_mode, S.E};
+        Scope sr(KC_RK); sr.done(S.L->rk(r, S.st));
     }
     return 0;
 }
@@ -402,7 +431,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         }
     }
     if (p->weno_order != 5) return fail(MFC_B200_EUNSUPPORTED, "weno_order 1 and 3 are not built yet (SURVEY.md 8f-3)");
-    if (visc) return fail(MFC_B200_EUNSUPPORTED, "viscous fluxes are not built yet (SURVEY.md 8a-8)");
+    if (visc && nd == 3) return fail(MFC_B200_EUNSUPPORTED, "viscous fluxes exist in 1D/2D only (the reference has no 3D; the 3D extension is inviscid)");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -418,10 +447,15 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     for (int d = 0; d < 3; d++) S.p.cb[d] = S.p.cc[d] = S.p.ds[d] = nullptr;    // never keep host pointers
     S.nf = nf; S.nd = nd; S.E = p->sys_size; S.b = p->buff_size; S.viscous = visc;
     S.L = p->strict_math ? &launchers_strict() : &launchers_fast();
+    S.Re_size[0] = S.Re_size[1] = 0;                                   // m_global_parameters.fpp:314-339, m_rhs.fpp:385-390
+    for (int i = 0; i < nf; i++)
+        for (int k = 0; k < 2; k++)
+            if (p->Re[i][k] > 0.0) { S.Re_idx[k][S.Re_size[k]] = i; S.Res[k][S.Re_size[k]] = p->Re[i][k]; S.Re_size[k]++; }
     {
         const char *e = std::getenv("MFC_B200_KERNELS");
         S.variant = (e && e[0] == '1') ? 1 : 2;
     }
+    if (visc && S.variant != 2) return fail(MFC_B200_EUNSUPPORTED, "the v1 sweep kernels (MFC_B200_KERNELS=1) have no viscous path");
     S.g = make_grid(p->m, p->n, p->p, nd, S.b);
     if (S.g.fstride >= (1LL << 32)) return fail(MFC_B200_EUNSUPPORTED, "more than 2^32 elements per field (kernels use 32-bit in-plane offsets)");
     for (int d = 0; d < 3; d++)
@@ -441,6 +475,10 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         for (int i = 0; i < 3; i++)
             if ((rc = make_tmap(S.tm_state[i][w], S.state[i], w == 0 ? kWX : kWY))) return rc;
         if ((rc = make_tmap(S.tm_rhs[w], S.rhs, w == 0 ? kWX : kWY))) return rc;
+    }
+    if (visc) {
+        CK(cudaMalloc(&S.visc_face, field_bytes()*(nd + 2))); CK(cudaMemsetAsync(S.visc_face, 0, field_bytes()*(nd + 2), S.st));
+        CK(cudaMalloc(&S.visc_grad, field_bytes()*nd*nd)); CK(cudaMemsetAsync(S.visc_grad, 0, field_bytes()*nd*nd, S.st));
     }
     CK(cudaMalloc(&S.stab_dev, 3*sizeof(unsigned long long)));
     CK(cudaMallocHost(&S.stab_host, 3*sizeof(unsigned long long)));
@@ -473,6 +511,8 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         CK(cudaMalloc(&S.ds[d], r.size()*sizeof(double)));
         CK(cudaMemcpy(S.rds[d], r.data(), r.size()*sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(S.ds[d], p->ds[d], r.size()*sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&S.cc[d], r.size()*sizeof(double)));
+        CK(cudaMemcpy(S.cc[d], p->cc[d], r.size()*sizeof(double), cudaMemcpyHostToDevice));
         for (int s = 0; s < 2; s++)
             if (S.bc[d][s] >= 0) {
                 const size_t n = (size_t)slab_count(S.g, d)*S.E*sizeof(double);

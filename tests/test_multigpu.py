@@ -28,8 +28,9 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("nproc,names", [(2, ["sod_1d", "shockbubble_2d", "shearlayer_2d", "shockdroplet_2d", "shockbubble_3d"]),
-                                         (4, ["shockbubble_2d", "shearlayer_2d", "shockbubble_3d"]),
+@pytest.mark.parametrize("nproc,names", [(2, ["sod_1d", "shockbubble_2d", "shearlayer_2d", "shockdroplet_2d", "shockbubble_3d", "viscous_2d",
+                                              "shockdroplet_2d_viscous"]),
+                                         (4, ["shockbubble_2d", "shearlayer_2d", "shockbubble_3d", "viscous_2d", "shockdroplet_2d_viscous"]),
                                          (8, ["shockbubble_3d"])])
 def test_nccl_halo_exchange_matches_single_rank_oracle(nproc, names):
     if _ngpu() < nproc:
