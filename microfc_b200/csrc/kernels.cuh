@@ -547,6 +547,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #define MFC_WARPS_Y 4
 #define MFC_CTAS_Y 4
 #endif
+#ifndef MFC_RING_Z
+#define MFC_RING_Z 8
+#define MFC_CTAS_Z 3
+#endif
 #ifndef MFC_RING_X
 #define MFC_RING_X 4
 #define MFC_WARPS_X 4
@@ -558,16 +562,22 @@ constexpr int kWarpCells = 30; // cells finished per warp and row in the x kerne
 // doubles per ring slot: E rows of W doubles, padded so that every slot starts on a 128-byte line
 // (the TMA destination alignment)
 __host__ __device__ constexpr int slot_doubles(int E, int W) { return (E*W + 15)/16*16; }
-// Occupancy (measured at 512^3, profiles/r01_tune_occupancy.txt): x 5 CTAs x 4 warps (<= 96
-// registers, 40 KB of rings per CTA), y/z 4 CTAs x 4 warps (<= 128 registers, 6-slot rings,
-// 48 KB per CTA) is the fastest of the variants tried; 15 or 18 warps per SM with fewer
-// registers are slower.
-#ifndef MFC_MARCH_UNROLL
-#define MFC_MARCH_UNROLL 1
+// Occupancy (measured at 512^3, profiles/r01_tune_occupancy.txt, r01_v3b_tune_pingpong_occupancy.txt):
+// x 5 CTAs x 4 warps (<= 96 registers, 40 KB of rings per CTA), y 4 CTAs x 4 warps (<= 128
+// registers, 6-slot rings), last direction (fused RK update, more live values) 3 CTAs x 4 warps
+// (<= 168 registers, 8-slot rings).
+#ifndef MFC_MARCH_PINGPONG
+// 1: two march iterations per loop trip with the carried face state in swapped register sets (no
+// copies, 6 % fewer instructions) -- measured SLOWER at 512^3 (y 7.9 vs 6.1 ms, z 11.1 vs 6.9 ms,
+// profiles/r01_v3b_tune_pingpong_occupancy.txt): the doubled loop body no longer fits the
+// instruction cache.  Kept for reference, off by default.
+#define MFC_MARCH_PINGPONG 0
 #endif
-constexpr int kMarchUnroll = MFC_MARCH_UNROLL;   // unrolling the march renames the carried face state instead of copying it
 constexpr int kWarpsX = MFC_WARPS_X, kCtasX = MFC_CTAS_X;
 constexpr int kWarpsY = MFC_WARPS_Y, kCtasY = MFC_CTAS_Y;
+// the last direction carries the fused RK update (more live registers): its own occupancy knobs
+__host__ __device__ constexpr int march_ring(int dir, int nd) { return dir == nd - 1 ? MFC_RING_Z : kRingY; }
+__host__ __device__ constexpr int march_ctas(int dir, int nd) { return dir == nd - 1 ? MFC_CTAS_Z : kCtasY; }
 
 // cons -> prim of one cell held in a ring slot (stride LD between variables), in place:
 // momenta become velocities, the energy becomes the pressure (:187-227, :353-362, :98-106)
@@ -770,9 +780,10 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
 // per variable and row, issued by lane 0 three rows ahead of the compute; mbarrier per slot).
 // No block-wide barrier exists, so warps never wait for each other.  Within a row the work is
 // the warp-shuffle pencil of v1: lane = cell, neighbours' face states / fluxes by shuffle.
-// BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).
+// BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).  VISC: viscous run,
+// vel_src and Re_avg of every face are stored for k_visc.
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int COEF, bool BC4>
+template <int NF, int ND, int COEF, bool BC4, bool VISC>
 __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = slot_doubles(E, kWX);
     constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
@@ -871,7 +882,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
         double F[E], uf;
         double vs[ND];
         hllc<NF, ND, 0>(vR, Rs, a.gammas, a.pi_infs, F, uf, vs);
-        if (a.visc_face != nullptr && lane <= kWarpCells && j_raw <= g.N[0])   // faces -1/2 .. N+1/2, keyed by the left cell
+        if (VISC && lane <= kWarpCells && j_raw <= g.N[0])   // faces -1/2 .. N+1/2, keyed by the left cell
             store_visc_face<NF, ND>(a, off, vR, Rs, vs);
         double Fm[E], ufm;
 #pragma unroll
@@ -897,9 +908,9 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 // is handed back to the TMA engine.  Lanes beyond the domain compute on whatever their ring
 // column holds and never store.
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR, int COEF, bool BC4>
-__global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, R = kRingY, SLOT = slot_doubles(E, kWY);
+template <int NF, int ND, int DIR, int COEF, bool BC4, bool VISC>
+__global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march2(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
     static_assert(R >= 6, "the ring holds the 5 live rows of the stencil plus at least one row in flight");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -915,7 +926,8 @@ __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_cons
     const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
     const long long ss = DIR == 1 ? g.sy : g.sz;
     const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the warp's columns
-    const int r_first = s0 - 3, r_last = s1 + 3;
+    // rows s0-3 .. s1+3 (+1 when the ping-pong loop pads the iteration count to an even number)
+    const int r_first = s0 - 3, r_last = s1 + 3 + (MFC_MARCH_PINGPONG ? ((s1 - s0 + 3) & 1) : 0);
     if (lane == 0) {
         for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
@@ -946,15 +958,16 @@ __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_cons
     const double *p0 = ring + lane, *p1 = p0 + SLOT, *p2 = p1 + SLOT, *p3 = p2 + SLOT, *p4 = p3 + SLOT;
     const double *const ring_end = ring + R*SLOT;
 
-    double vRp[E], Fp[E], ufp = 0.0;
-#pragma unroll
-    for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
     const unsigned uss = (unsigned)ss;
     // plane-relative element offset of cell s-1 of my column (lanes beyond the domain: column N)
     unsigned off = (unsigned)(base + (min(j0 + lane, g.N[0]) - j0) + (long long)(s0 - 3)*ss);
     Weno<COEF> weno;
-#pragma unroll kMarchUnroll
-    for (int s = s0 - 1; s <= s1 + 1; s++) {
+    // One iteration of the march: reconstruct cell s, solve face s-1/2 against the right-face
+    // state carried from cell s-1 (vRi), finish cell s-1 with the flux carried from face s-3/2
+    // (Fi, ufi).  The carried values go OUT in different registers (vRo, Fo, ufo): the loop below
+    // calls the body twice with the two sets swapped, so nothing is copied between iterations.
+    auto body = [&](const int s, const bool real, const double (&vRi)[E], const double (&Fi)[E], const double ufi,
+                    double (&vRo)[E], double (&Fo)[E], double &ufo) {
         convert_next();                                // row s+2
         off += uss;
         const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
@@ -963,36 +976,34 @@ __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_cons
             if (RK && a.rk_mode >= (MFC_STRICT ? 1 : 2)) tma_prefetch_row(&a.tm_q1, cx, DIR == 1 ? cy + s : cy, DIR == 1 ? cz : cz + s);
         }
         weno.load(a, s);
-        double vL[E], vR[E];
+        double vL[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
             const double st[5] = {p0[v*kWY], p1[v*kWY], p2[v*kWY], p3[v*kWY], p4[v*kWY]};
-            weno(st, vL[v], vR[v]);
+            weno(st, vL[v], vRo[v]);
         }
         if (s >= s0) {
             CellIn<E, ACC, RK> in;
             if (fin) load_cell<NF, ND, ACC, RK>(a, off, in);
+            double Ls[BC4 ? E : 1];
             if (BC4) {
+#pragma unroll
+                for (int v = 0; v < E; v++) Ls[v] = vRi[v];
                 if (a.bc_beg == -4 && s == 0) {
 #pragma unroll
-                    for (int v = 0; v < E; v++) vRp[v] = vL[v];
+                    for (int v = 0; v < E; v++) Ls[v] = vL[v];
                 }
                 if (a.bc_end == -4 && s == g.N[DIR] + 1) {
 #pragma unroll
-                    for (int v = 0; v < E; v++) vL[v] = vRp[v];
+                    for (int v = 0; v < E; v++) vL[v] = Ls[v];
                 }
             }
-            double F[E], uf;
+            const double *L = BC4 ? Ls : vRi;
             double vs[ND];
-            hllc<NF, ND, DIR>(vRp, vL, a.gammas, a.pi_infs, F, uf, vs);
-            if (a.visc_face != nullptr && on) store_visc_face<NF, ND>(a, off, vRp, vL, vs);   // face s-1/2, left cell s-1
-            if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, off, on, a.rds[s - 1 + g.b], p1, in, Fp, ufp, F, uf);   // p1: row s-1
-#pragma unroll
-            for (int v = 0; v < E; v++) Fp[v] = F[v];
-            ufp = uf;
+            hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Fo, ufo, vs);
+            if (VISC && on && real) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
+            if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, off, on && real, a.rds[s - 1 + g.b], p1, in, Fi, ufi, Fo, ufo);   // p1: row s-1
         }
-#pragma unroll
-        for (int v = 0; v < E; v++) vRp[v] = vR[v];
         fence_proxy_async();
         __syncwarp();                                  // row s-2 is dead for the whole warp
         if (next_issue <= r_last) {
@@ -1003,7 +1014,27 @@ __global__ void __launch_bounds__(32*kWarpsY, kCtasY) k_march2(const __grid_cons
         p0 = p1; p1 = p2; p2 = p3; p3 = p4;
         p4 += SLOT;
         if (p4 >= ring_end) p4 -= R*SLOT;
+    };
+    double vRa[E], Fa[E], ufa = 0.0, vRb[E], Fb[E], ufb = 0.0;
+#pragma unroll
+    for (int v = 0; v < E; v++) { vRa[v] = 0.0; Fa[v] = 0.0; vRb[v] = 0.0; Fb[v] = 0.0; }
+#if MFC_MARCH_PINGPONG
+    // iterations s0-1 .. s1+1, padded to an even count with one masked iteration (its extra row
+    // s1+4 is at most the outermost ghost row, b >= 4)
+#pragma unroll 1
+    for (int s = s0 - 1; s <= s1 + 1; s += 2) {
+        body(s, true, vRa, Fa, ufa, vRb, Fb, ufb);
+        body(s + 1, s + 1 <= s1 + 1, vRb, Fb, ufb, vRa, Fa, ufa);
     }
+#else
+#pragma unroll 1
+    for (int s = s0 - 1; s <= s1 + 1; s++) {
+        body(s, true, vRa, Fa, ufa, vRb, Fb, ufb);
+#pragma unroll
+        for (int v = 0; v < E; v++) { vRa[v] = vRb[v]; Fa[v] = Fb[v]; }
+        ufa = ufb;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -66,6 +66,12 @@ struct Sim {
     bool viscous = false;
     const Launchers *L = nullptr;
     cudaStream_t st = nullptr;
+    // multi-rank: the halo exchange runs on its own stream so that the y / z exchanges overlap
+    // with the x sweep (inviscid runs: the three directions are independent, see ghosts_begin)
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_q = nullptr, ev_halo[3] = {nullptr, nullptr, nullptr};
+    bool halo_pending[3] = {false, false, false};
+    bool overlap = false;
     double *state[3] = {nullptr, nullptr, nullptr};
     int cur = 0;                       // which buffer holds q_cons_ts(1)
     const double *last_q = nullptr;    // state of the most recent RHS evaluation (what q_prim_vf reflects)
@@ -118,19 +124,20 @@ int fail(int code, const std::string &msg) { S.err = msg; return code; }
 
 // launch bookkeeping: count, optional per-class CUDA-event timing on the launching stream
 struct Scope {
-    int kc; ProfRec r{};
-    explicit Scope(int kc_) : kc(kc_) {
-        if (S.prof) { r.kc = kc; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, S.st); }
+    int kc; ProfRec r{}; cudaStream_t s;
+    explicit Scope(int kc_, cudaStream_t s_ = nullptr) : kc(kc_), s(s_ ? s_ : S.st) {
+        if (S.prof) { r.kc = kc; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, s); }
     }
     void done(int n) {
         S.launches += n;
-        if (S.prof) { cudaEventRecord(r.b, S.st); S.prof_recs.push_back(r); }
+        if (S.prof) { cudaEventRecord(r.b, s); S.prof_recs.push_back(r); }
     }
 };
 
 void prof_collect() {
     if (S.prof_recs.empty()) return;
     cudaStreamSynchronize(S.st);
+    if (S.cs) cudaStreamSynchronize(S.cs);
     for (auto &r : S.prof_recs) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
@@ -156,6 +163,10 @@ void free_all() {
     if (S.sv0) { cudaEventDestroy(S.sv0); S.sv0 = nullptr; }
     if (S.sv1) { cudaEventDestroy(S.sv1); S.sv1 = nullptr; }
     if (S.comm && S.nccl.CommDestroy) { S.nccl.CommDestroy(S.comm); S.comm = nullptr; }
+    if (S.ev_q) { cudaEventDestroy(S.ev_q); S.ev_q = nullptr; }
+    for (auto &e : S.ev_halo) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (S.cs) { cudaStreamDestroy(S.cs); S.cs = nullptr; }
+    S.overlap = false;
     if (S.st) { cudaStreamDestroy(S.st); S.st = nullptr; }
     for (auto &r : S.prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     S.prof_recs.clear();
@@ -197,40 +208,79 @@ const TensorMap *state_tmap(const double *q, int which) {
     return nullptr;
 }
 
-// ---- ghost cells: physical BCs (k_bc) and processor boundaries (pack / NCCL / unpack),
-// one direction after the other like m_rhs.fpp:686-908 ---------------------------------------
-int fill_ghosts(double *q) {
-    for (int d = 0; d < S.nd; d++) {
-        const bool phys = S.bc[d][0] < 0 || S.bc[d][1] < 0;
-        const bool proc = S.bc[d][0] >= 0 || S.bc[d][1] >= 0;
-        if (proc) {
-            if (!S.comm) return fail(MFC_B200_ESTATE, "processor boundary present but mfc_b200_comm_init was not called");
-            const long long n = slab_count(S.g, d)*S.E;
-            for (int s = 0; s < 2; s++) {
-                if (S.bc[d][s] < 0) continue;
-                HaloArgs h{S.g, q, S.sendbuf[d][s], d, s, S.E};
-                Scope sc(KC_PACK); sc.done(S.L->halo_pack(h, S.st));
-            }
-            // sends: [to beg: my first layers] [to end: my last layers];  receives in the
-            // opposite order so that two exchanges with the SAME peer (2 ranks, periodic)
-            // pair up correctly.
-            NK(S.nccl.GroupStart());
-            for (int s = 0; s < 2; s++)
-                if (S.bc[d][s] >= 0) NK(S.nccl.Send(S.sendbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, S.st));
-            for (int s = 1; s >= 0; s--)
-                if (S.bc[d][s] >= 0) NK(S.nccl.Recv(S.recvbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, S.st));
-            NK(S.nccl.GroupEnd());
-            for (int s = 0; s < 2; s++) {
-                if (S.bc[d][s] < 0) continue;
-                HaloArgs h{S.g, q, S.recvbuf[d][s], d, s, S.E};
-                Scope sc(KC_UNPACK); sc.done(S.L->halo_unpack(h, S.st));
-            }
-        }
-        if (phys) {
-            BcArgs a{S.g, q, d, S.E, S.nf + d, S.bc[d][0], S.bc[d][1]};
-            Scope sc(KC_BC); sc.done(S.L->bc(a, S.st));
-        }
+// ---- ghost cells: physical BCs (k_bc) and processor boundaries (pack / NCCL / unpack) --------
+// processor boundaries of direction d: pack, ncclSend/ncclRecv with the +-d neighbours, unpack
+// (m_mpi_proxy.fpp:468-979), all on stream st
+int exchange_dir(double *q, int d, cudaStream_t st) {
+    if (!S.comm) return fail(MFC_B200_ESTATE, "processor boundary present but mfc_b200_comm_init was not called");
+    const long long n = slab_count(S.g, d)*S.E;
+    for (int s = 0; s < 2; s++) {
+        if (S.bc[d][s] < 0) continue;
+        HaloArgs h{S.g, q, S.sendbuf[d][s], d, s, S.E};
+        Scope sc(KC_PACK, st); sc.done(S.L->halo_pack(h, st));
     }
+    // sends: [to beg: my first layers] [to end: my last layers];  receives in the opposite
+    // order so that two exchanges with the SAME peer (2 ranks, periodic) pair up correctly.
+    NK(S.nccl.GroupStart());
+    for (int s = 0; s < 2; s++)
+        if (S.bc[d][s] >= 0) NK(S.nccl.Send(S.sendbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, st));
+    for (int s = 1; s >= 0; s--)
+        if (S.bc[d][s] >= 0) NK(S.nccl.Recv(S.recvbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, st));
+    NK(S.nccl.GroupEnd());
+    for (int s = 0; s < 2; s++) {
+        if (S.bc[d][s] < 0) continue;
+        HaloArgs h{S.g, q, S.recvbuf[d][s], d, s, S.E};
+        Scope sc(KC_UNPACK, st); sc.done(S.L->halo_unpack(h, st));
+    }
+    return 0;
+}
+int physical_bc_dir(double *q, int d) {
+    if (S.bc[d][0] >= 0 && S.bc[d][1] >= 0) return 0;
+    BcArgs a{S.g, q, d, S.E, S.nf + d, S.bc[d][0], S.bc[d][1]};
+    Scope sc(KC_BC); sc.done(S.L->bc(a, S.st));
+    return 0;
+}
+
+// Ghost fill of the stage state, m_rhs.fpp:686-908.
+//   sequential (single rank, viscous, v1 kernels): one direction after the other on the compute
+//     stream, later directions covering the ghosts of the earlier ones (corners), like the reference.
+//   overlapped (multi-rank inviscid v2 path): a sweep along d reads ghosts of direction d only,
+//     at interior transverse indices -- corner ghosts are never read -- so the three exchanges
+//     are independent.  They are enqueued on the communication stream in the order x, y, z; the
+//     sweep along d waits for exchange d only (ghosts_ready), i.e. the y and z exchanges run
+//     under the x sweep.  Interior results are identical to the sequential order bit for bit.
+int ghosts_begin(double *q) {
+    for (int d = 0; d < 3; d++) S.halo_pending[d] = false;
+    if (!S.overlap) {
+        for (int d = 0; d < S.nd; d++) {
+            int rc;
+            if ((S.bc[d][0] >= 0 || S.bc[d][1] >= 0) && (rc = exchange_dir(q, d, S.st))) return rc;
+            if ((rc = physical_bc_dir(q, d))) return rc;
+        }
+        return 0;
+    }
+    CK(cudaEventRecord(S.ev_q, S.st));
+    CK(cudaStreamWaitEvent(S.cs, S.ev_q, 0));
+    for (int d = 0; d < S.nd; d++) {
+        if (S.bc[d][0] < 0 && S.bc[d][1] < 0) continue;
+        int rc;
+        if ((rc = exchange_dir(q, d, S.cs))) return rc;
+        CK(cudaEventRecord(S.ev_halo[d], S.cs));
+        S.halo_pending[d] = true;
+    }
+    return 0;
+}
+// ghosts of direction d complete on the compute stream (overlapped mode; no-op otherwise)
+int ghosts_ready(double *q, int d) {
+    if (!S.overlap) return 0;
+    if (S.halo_pending[d]) { CK(cudaStreamWaitEvent(S.st, S.ev_halo[d], 0)); S.halo_pending[d] = false; }
+    return physical_bc_dir(q, d);
+}
+int fill_ghosts(double *q) {
+    int rc;
+    if ((rc = ghosts_begin(q))) return rc;
+    for (int d = 0; d < S.nd; d++)
+        if ((rc = ghosts_ready(q, d))) return rc;
     return 0;
 }
 
@@ -302,7 +352,9 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     // the primitive variables of the previous RHS evaluation (m_time_steppers.fpp:288-290).
     if (stop && S.p.run_time_info && want_stab && S.last_q)
         if ((rc = run_stability(S.last_q, dt))) return rc;
-    if ((rc = fill_ghosts(q))) return rc;                    // m_rhs.fpp:435
+    // m_rhs.fpp:435.  Anything that reads the whole ghosted box needs every direction complete.
+    const bool need_all = stop || S.variant != 2 || S.viscous;
+    if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
     // :445-447 (v2: fused into the sweeps; the viscous kernels read the velocity planes)
     if ((S.variant != 2 || S.viscous) && (rc = run_prim(q))) return rc;
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
@@ -311,7 +363,12 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     // itself from the primitive variables it already holds (no extra pass over the state).
     const bool do_stab = first_stage && S.p.run_time_info && want_stab;
     const bool fuse_stab = do_stab && S.variant == 2 && !S.p.strict_math && !S.viscous;
-    if (do_stab && !fuse_stab && (rc = run_stability(q, dt))) return rc;
+    if (do_stab && !fuse_stab) {
+        if (!need_all)
+            for (int d = 0; d < S.nd; d++)
+                if ((rc = ghosts_ready(q, d))) return rc;
+        if ((rc = run_stability(q, dt))) return rc;
+    }
     if (fuse_stab && (rc = stab_reset())) return rc;
     ViscArgs va{};
     if (S.viscous) {                                         // :456-464 s_get_viscous
@@ -339,6 +396,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
+        if ((rc = ghosts_ready(q, d))) return rc;
         {
             const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
             if (!tq || !t1) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
@@ -541,6 +599,13 @@ int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
     ncclUniqueId u;
     std::memcpy(&u, id, 128);
     NK(S.nccl.CommInitRank(&S.comm, nranks, u, rank));
+    CK(cudaStreamCreateWithFlags(&S.cs, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&S.ev_q, cudaEventDisableTiming));
+    for (auto &e : S.ev_halo) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        const char *e = std::getenv("MFC_B200_OVERLAP");       // 0 disables (for A/B measurements)
+        S.overlap = S.variant == 2 && !S.viscous && !(e && e[0] == '0');
+    }
     return 0;
 }
 

@@ -15,7 +15,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 from microfc_b200 import cases, pre_process  # noqa: E402
 from microfc_b200.simulation import Simulation  # noqa: E402
-from common import norm_linf, oracle_run  # noqa: E402
+from common import norm_linf, oracle_run, roundoff_sensitivity  # noqa: E402
 
 CASES = {
     "sod_1d": (lambda: cases.sod_1d(Nx=199), 40),
@@ -68,7 +68,12 @@ def main():
                         good = good and all(a[2][0] == b[2][0] for a, b in zip(rows, rows_ref))
                 else:
                     err = norm_linf(out, ref, cfg)
-                    good = bool((err <= 1e-10).all())
+                    tol = 1e-10
+                    if (err > tol).any():
+                        # badly conditioned case (stiffened-gas liquid): same rule as tests/test_gpu_parity.py --
+                        # the oracle itself must move comparably under a 1-ulp perturbation of its input
+                        tol = max(tol, 4.0*roundoff_sensitivity(cfg, cb, q0, ref).max())
+                    good = bool((err <= tol).all())
                 print(f"{name} world={world} strict={strict}: {'OK' if good else 'MISMATCH ' + str(norm_linf(out, ref, cfg))}", flush=True)
                 ok = ok and good
     dist.barrier()

@@ -14,10 +14,10 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     # name: (RING_Y, WARPS_Y, CTAS_Y, RING_X, WARPS_X, CTAS_X, extra -D flags)
-    "y6w4c4_x4w4c5_u2": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_UNROLL=2"),
-    "y6w4c4_x4w4c5_u1": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_UNROLL=1"),
-    "y8w4c3_x4w4c4_u1": (8, 4, 3, 4, 4, 4, "-DMFC_MARCH_UNROLL=1"),
-    "y8w4c3_x4w4c4_u2": (8, 4, 3, 4, 4, 4, "-DMFC_MARCH_UNROLL=2"),
+    "pp_z4": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_PINGPONG=1"),
+    "pp_z3r8": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_PINGPONG=1 -DMFC_RING_Z=8 -DMFC_CTAS_Z=3"),
+    "nopp_z3r8": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_PINGPONG=0 -DMFC_RING_Z=8 -DMFC_CTAS_Z=3"),
+    "pp_y3z3r8": (8, 4, 3, 4, 4, 5, "-DMFC_MARCH_PINGPONG=1 -DMFC_RING_Z=8 -DMFC_CTAS_Z=3"),
 }
 
 
