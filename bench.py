@@ -297,8 +297,24 @@ def main():
     last_dir = {1: "k_sweep_x", 2: "k_sweep_march<y>", 3: "k_sweep_march<z>"}[nd]
     cells_gpu = ncell_total // args.gpus
     dom_flops = sweep_flops_per_cell(E, nd, dom == last_dir) * cells_gpu
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_v3a_traffic.json")
+    if os.path.exists(tp) and nd == 3 and E == 8:
+        # DRAM bytes per cell of this kernel from the committed ncu --set full capture (256^3, same
+        # kernels): one stage-1 launch and two stage-2/3 launches per step
+        tj = json.load(open(tp))
+        k1, k2 = tj["kernels"].get(dom + "/stage1"), tj["kernels"].get(dom + "/stage2")
+        if k1 and k2:
+            traffic = (k1["dram_bytes_per_cell"] + 2 * k2["dram_bytes_per_cell"]) / 3 * cells_gpu
+            traffic_src = tj["source"]
+    per_kernel = {}
+    for k, (sec, n) in sweeps.items():
+        fl = sweep_flops_per_cell(E, nd, k == last_dir) * cells_gpu
+        per_kernel[k] = {"avg_launch_ms": sec / n * 1e3, "fp64_tflops_algorithmic": fl / (sec / n) / 1e12,
+                         "frac_fp64": fl / (sec / n) / 1e12 / fp64_peak}
     roof = {"bound": "fp64", "kernel": dom, "achieved": dom_flops / dom_t / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": dom_flops / dom_t / 1e12 / fp64_peak, "traffic": None,
+            "frac": dom_flops / dom_t / 1e12 / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+            "per_kernel": per_kernel,
             "avg_launch_ms": dom_t * 1e3, "algorithmic_flops_per_cell": sweep_flops_per_cell(E, nd, dom == last_dir),
             "peak_source": fp64_src,
             "note": "FP64-vector-pipe roof (no tensor cores on this path); algorithmic flops = source count of the reference "
