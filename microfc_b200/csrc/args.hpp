@@ -32,6 +32,7 @@ struct SweepArgs {
     // cells this kernel finishes, m_data_output.fpp:215-233; nullptr = off
     unsigned long long *stab_out;
     const double *rds_t[2];      // 1/ds of the two transverse directions (y, z)
+    int weno_order;        // 5, 3 or 1
     int variant;           // 2: TMA-ring kernels (k_xrow / k_march2), 1: v1 direct-load kernels
     int coef_uniform;      // 1: cuni[] holds the coefficients of every cell of this direction
     double cuni[kNumWenoCoef];   // uniform-grid WENO coefficients (COEF = 0 kernels)

@@ -177,6 +177,36 @@ __device__ __forceinline__ void weno5(const double v[5], const double c[27], dou
 }
 
 // ------------------------------------------------------------------------------------------
+// WENO3 on the 3-cell stencil v[1..3] = v(j-1..j+1), m_weno.fpp:416-466; coefficient slots as
+// filled by weno3_cell (weno_coefficients.cpp).  WENO1 (:391-414) is vL = vR = v(j).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void weno3(const double v[5], const double c[27], double eps, double &vL, double &vR) {
+    const double dvd0 = v[3] - v[2];                                   // dvd(0)  :420
+    const double dvdm1 = v[2] - v[1];                                  // dvd(-1) :422
+    const double pl0 = v[2] + c[0]*dvd0, pl1 = v[2] + c[2]*dvdm1;      // :425-428
+    const double pr0 = v[2] + c[6]*dvd0, pr1 = v[2] + c[8]*dvdm1;      // :446-449
+    const double b0 = c[18]*dvd0*dvd0 + eps;                           // :430-433
+    const double b1 = c[21]*dvdm1*dvdm1 + eps;
+#if MFC_STRICT
+    double a0 = c[12]/(b0*b0), a1 = c[13]/(b1*b1);                     // :435
+    double s = a0 + a1;
+    double w0 = a0/s, w1 = a1/s;                                       // :437
+    vL = w0*pl0 + w1*pl1;                                              // :441
+    a0 = c[15]/(b0*b0); a1 = c[16]/(b1*b1);                            // :451
+    s = a0 + a1;
+    w0 = a0/s; w1 = a1/s;                                              // :453
+    vR = w0*pr0 + w1*pr1;                                              // :457
+#else
+    const double q0 = b0*b0, q1 = b1*b1;                               // omega_k = d_k q_l/(d_0 q_1 + d_1 q_0)
+    const double aL0 = c[12]*q1, aL1 = c[13]*q0, aR0 = c[15]*q1, aR1 = c[16]*q0;
+    const double DL = aL0 + aL1, DR = aR0 + aR1;
+    const double inv = rcp_fast3(DL*DR);
+    vL = fma(aL0, pl0, aL1*pl1)*(DR*inv);
+    vR = fma(aR0, pr0, aR1*pr1)*(DL*inv);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
 // HLLC flux at one face, m_riemann_solvers.fpp:136-325.  L/R are the reconstructed primitive
 // states [alpha_rho(NF) | vel(ND) | pres | alpha(NF)] left and right of the face; NRM is the
 // sweep direction (dir_idx(1), :464-470).  dir_flg is folded in exactly: it is 0 or 1, and
@@ -618,21 +648,24 @@ __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, 
 
 // reconstruction of one variable at one cell: uniform-grid constants (COEF = 0, fast build only)
 // or the per-cell coefficient tables (m_weno.fpp:223-347)
-template <int COEF>
+// WO = weno_order (5, 3 or 1; the lower orders always use the tables)
+template <int COEF, int WO>
 struct Weno {
-    static constexpr bool kUniform = COEF == 0 && !MFC_STRICT;
-    double c[kUniform ? 1 : 27];
+    static constexpr bool kUniform = COEF == 0 && !MFC_STRICT && WO == 5;
+    double c[(kUniform || WO == 1) ? 1 : 27];
     double eps;
     __device__ __forceinline__ void load(const SweepArgs &a, int cell) {
         if (kUniform) {
             eps = 3.0*a.eps;
         } else {
-            load_coef(a, cell, c);
+            if (WO != 1) load_coef(a, cell, c);
             eps = a.eps;
         }
     }
     __device__ __forceinline__ void operator()(const double s[5], double &vL, double &vR) const {
-        if (kUniform) weno5_uniform(s, eps, vL, vR);
+        if (WO == 1) { vL = s[2]; vR = s[2]; }
+        else if (WO == 3) weno3(s, c, eps, vL, vR);
+        else if (kUniform) weno5_uniform(s, eps, vL, vR);
         else weno5(s, c, eps, vL, vR);
     }
 };
@@ -783,7 +816,7 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
 // BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).  VISC: viscous run,
 // vel_src and Re_avg of every face are stored for k_visc.
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int COEF, bool BC4, bool VISC>
+template <int NF, int ND, int COEF, bool BC4, bool VISC, int WO>
 __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = slot_doubles(E, kWX);
     constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
@@ -813,7 +846,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
     const int j_raw = jw - 1 + lane;
     const int j = min(j_raw, g.N[0] + 1);              // clamped lanes never store
     const int sx = j - x0;                             // staged index of my cell (3 .. 34)
-    Weno<COEF> weno;
+    Weno<COEF, WO> weno;
     weno.load(a, j);
     const double rds = a.rds[j + g.b];
     const unsigned full = 0xffffffffu;
@@ -908,7 +941,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 // is handed back to the TMA engine.  Lanes beyond the domain compute on whatever their ring
 // column holds and never store.
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR, int COEF, bool BC4, bool VISC>
+template <int NF, int ND, int DIR, int COEF, bool BC4, bool VISC, int WO>
 __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march2(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
@@ -961,7 +994,7 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march2(cons
     const unsigned uss = (unsigned)ss;
     // plane-relative element offset of cell s-1 of my column (lanes beyond the domain: column N)
     unsigned off = (unsigned)(base + (min(j0 + lane, g.N[0]) - j0) + (long long)(s0 - 3)*ss);
-    Weno<COEF> weno;
+    Weno<COEF, WO> weno;
     // One iteration of the march: reconstruct cell s, solve face s-1/2 against the right-face
     // state carried from cell s-1 (vRi), finish cell s-1 with the flux carried from face s-3/2
     // (Fi, ufi).  The carried values go OUT in different registers (vRo, Fo, ufo): the loop below

@@ -392,7 +392,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
             a.Re_size[i] = S.Re_size[i];
             for (int k = 0; k < kMaxFluids; k++) { a.Res[i][k] = S.Res[i][k]; a.Re_idx[i][k] = S.Re_idx[i][k]; }
         }
-        a.variant = S.variant; a.coef_uniform = S.coef_uniform[d];
+        a.variant = S.variant; a.coef_uniform = S.coef_uniform[d]; a.weno_order = S.p.weno_order;
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
@@ -488,7 +488,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
             if (c < -12 || c >= p->num_procs) return fail(MFC_B200_EINVAL, "Unsupported value of bc. Exiting ...");
         }
     }
-    if (p->weno_order != 5) return fail(MFC_B200_EUNSUPPORTED, "weno_order 1 and 3 are not built yet (SURVEY.md 8f-3)");
+    if (p->weno_order != 5 && visc) return fail(MFC_B200_EUNSUPPORTED, "viscous fluxes are built for weno_order = 5 only");
     if (visc && nd == 3) return fail(MFC_B200_EUNSUPPORTED, "viscous fluxes exist in 1D/2D only (the reference has no 3D; the 3D extension is inviscid)");
 
     int ndev = 0;
@@ -513,7 +513,8 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         const char *e = std::getenv("MFC_B200_KERNELS");
         S.variant = (e && e[0] == '1') ? 1 : 2;
     }
-    if (visc && S.variant != 2) return fail(MFC_B200_EUNSUPPORTED, "the v1 sweep kernels (MFC_B200_KERNELS=1) have no viscous path");
+    if ((visc || p->weno_order != 5) && S.variant != 2)
+        return fail(MFC_B200_EUNSUPPORTED, "the v1 sweep kernels (MFC_B200_KERNELS=1) have no viscous / WENO1 / WENO3 path");
     S.g = make_grid(p->m, p->n, p->p, nd, S.b);
     if (S.g.fstride >= (1LL << 32)) return fail(MFC_B200_EUNSUPPORTED, "more than 2^32 elements per field (kernels use 32-bit in-plane offsets)");
     for (int d = 0; d < 3; d++)
@@ -543,7 +544,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     CK(cudaMallocHost(&S.stab_init, 3*sizeof(unsigned long long)));
     for (int d = 0; d < nd; d++) {
         const int N = S.g.N[d], b = S.b;
-        WenoTable t = build_weno5_table(p->cb[d], N, b);
+        WenoTable t = build_weno_table(p->cb[d], N, b, p->weno_order);
         S.clen[d] = t.len; S.coef_lo[d] = t.lo; S.h_coef[d] = t.data;
         {   // uniform grid?  then every cell's coefficients equal the classical WENO5-JS rationals
             // to rounding, and the fast kernels use those as compile-time constants
@@ -559,7 +560,7 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
                 for (int i = 0; i < t.len && uni; i++)
                     if (std::fabs(t.data[(size_t)c*t.len + i] - classic[c]) > 1e-12) uni = false;
             }
-            S.coef_uniform[d] = uni ? 1 : 0;
+            S.coef_uniform[d] = (uni && p->weno_order == 5) ? 1 : 0;
         }
         CK(cudaMalloc(&S.coef[d], t.data.size()*sizeof(double)));
         CK(cudaMemcpyAsync(S.coef[d], S.h_coef[d].data(), t.data.size()*sizeof(double), cudaMemcpyHostToDevice, S.st));

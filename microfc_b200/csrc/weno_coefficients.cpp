@@ -50,17 +50,40 @@ static void weno5_cell(const double *xb, double *out) {
     bt[8] = h2*(10.0*sq(w) + sq(d(0, -1)) + d(0, -1)*w)/(sq(d(-2, 0))*sq(d(-2, 1)));
 }
 
-WenoTable build_weno5_table(const double *cb, int N, int b) {
-    // cb -> s_cb(-1-b : N+b); cells -b+2 .. N+b-2 (m_weno.fpp:118-127 with weno_polyn = 2)
+// WENO3, m_weno.fpp:193-217.  xb[0..3] = s_cb(i-1 .. i+2).  The two candidate stencils use the
+// slots of k = 0, 1 / q = 0 of the 27-slot layout (poly [k*2], d [k], beta [k*3]); the rest is 0.
+static void weno3_cell(const double *xb, double *out) {
+    auto d = [xb](int a, int c) { return xb[a + 1] - xb[c + 1]; };
+    auto sq = [](double x) { return x*x; };
+    for (int c = 0; c < kNumWenoCoef; c++) out[c] = 0.0;
+    double *pL = out, *pR = out + 6, *dL = out + 12, *dR = out + 15, *bt = out + 18;
+    pR[0] = d(0, 1)/d(0, 2);
+    pR[2] = d(0, 1)/d(-1, 1);
+    pL[0] = -pR[0];
+    pL[2] = -pR[2];
+    dR[0] = d(-1, 1)/d(-1, 2);
+    dL[0] = d(-1, 0)/d(-1, 2);
+    dR[1] = 1.0 - dR[0];
+    dL[1] = 1.0 - dL[0];
+    bt[0] = 4.0*sq(d(0, 1))/sq(d(0, 2));
+    bt[3] = 4.0*sq(d(0, 1))/sq(d(-1, 1));
+}
+
+WenoTable build_weno_table(const double *cb, int N, int b, int weno_order) {
+    // cb -> s_cb(-1-b : N+b); cells -b+polyn .. N+b-polyn (m_weno.fpp:118-127)
+    const int polyn = (weno_order - 1)/2;
     WenoTable t;
-    t.lo = -b + 2;
-    t.len = N + 1 + 2*b - 4;
+    t.lo = -b + polyn;
+    t.len = N + 1 + 2*b - 2*polyn;
     t.data.assign((size_t)kNumWenoCoef*t.len, 0.0);
+    if (weno_order == 1) return t;                    // :105, first order needs no coefficients
     double tmp[kNumWenoCoef];
     for (int n = 0; n < t.len; n++) {
         const int cell = t.lo + n;
         const int i = cell - 1;                       // left boundary index of the cell
-        weno5_cell(cb + (i - 2) + 1 + b, tmp);        // element index of s_cb(x) is x + 1 + b
+        // element index of s_cb(x) is x + 1 + b
+        if (weno_order == 5) weno5_cell(cb + (i - 2) + 1 + b, tmp);
+        else weno3_cell(cb + (i - 1) + 1 + b, tmp);
         for (int c = 0; c < kNumWenoCoef; c++) t.data[(size_t)c*t.len + n] = tmp[c];
     }
     return t;

@@ -11,6 +11,6 @@ struct WenoTable {
 };
 
 // cb -> ghosted cell boundaries s_cb(-1-b : N+b) of one direction
-WenoTable build_weno5_table(const double *cb, int N, int b);
+WenoTable build_weno_table(const double *cb, int N, int b, int weno_order);
 
 }  // namespace mfc

@@ -25,6 +25,11 @@ CASES = {
     "viscous_2d_weno": lambda: cases.viscous_2d(N=49, weno_Re_flux=True),
     "viscous_2d_fd": lambda: cases.viscous_2d(N=49, weno_Re_flux=False),
     "shockdroplet_2d_viscous": lambda: cases.shockdroplet_2d(Nx=199, Ny=59, viscous=True),
+    # lower reconstruction orders and RK1 / RK2 (examples/1D_vacuum uses WENO3)
+    "vacuum_1d_weno3": lambda: cases.vacuum_1d(),
+    "sod_1d_weno1_rk1": lambda: dict(cases.sod_1d(), weno_order=1, time_stepper=1),
+    "shockbubble_2d_weno3_rk2": lambda: dict(cases.shockbubble_2d(Ny=60), weno_order=3, time_stepper=2),
+    "shockbubble_3d_weno3": lambda: dict(cases.shockbubble_3d(nc=32), weno_order=3),
 }
 
 
