@@ -282,7 +282,7 @@ def main():
         ts = 0
         for _ in range(K):
             sim.step(ts, dt); ts += 1            # 24 B of stability data D2H every step
-        sim.download(out_ghosted=host)           # D2H into pinned host memory
+        sim.download_ghosted(host)               # D2H into the host's (pinned) ghosted fields
         sim.sync(); barrier()
         e2e_secs = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": ncell_total * K / e2e_secs / 1e6, "unit": "Mcell-steps/s",

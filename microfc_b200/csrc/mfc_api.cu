@@ -439,14 +439,23 @@ int do_step(int t_step, double dt, bool stab) {
     return 0;
 }
 
-// host field (Fortran sf(-b:m+b, ...), x fastest, contiguous) <-> padded device plane
-int copy_field(double *dev_plane, const double *host, bool to_device, cudaStream_t st) {
+// host field (Fortran sf(-b:m+b, ...), x fastest, contiguous) <-> padded device plane.  The
+// host array crosses PCIe as ONE contiguous copy into a staging plane (the RHS accumulator, which
+// is scratch between steps) and is re-pitched on the device; a strided 2-D copy of 4 KB rows
+// straight from host memory reaches only ~8 GB/s.
+int copy_field(double *dev_plane, const double *host, bool to_device, cudaStream_t st, int v) {
     const GridDesc &g = S.g;
     const size_t w = (size_t)(g.N[0] + 1 + 2*g.b)*sizeof(double);
     double *d0 = dev_plane + (kXoff - g.b);
     const size_t rows = (size_t)g.ey*g.ez;
-    if (to_device) CK(cudaMemcpy2DAsync(d0, (size_t)g.pitch*sizeof(double), host, w, w, rows, cudaMemcpyHostToDevice, st));
-    else CK(cudaMemcpy2DAsync(const_cast<double *>(host), w, d0, (size_t)g.pitch*sizeof(double), w, rows, cudaMemcpyDeviceToHost, st));
+    double *stage = S.rhs + (size_t)v*g.fstride;         // w*rows <= fstride*8 bytes
+    if (to_device) {
+        CK(cudaMemcpyAsync(stage, host, w*rows, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpy2DAsync(d0, (size_t)g.pitch*sizeof(double), stage, w, w, rows, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CK(cudaMemcpy2DAsync(stage, w, d0, (size_t)g.pitch*sizeof(double), w, rows, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(const_cast<double *>(host), stage, w*rows, cudaMemcpyDeviceToHost, st));
+    }
     return 0;
 }
 
@@ -613,7 +622,7 @@ int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
 int mfc_b200_upload(const double *const q_cons[]) {
     if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_upload before mfc_b200_init");
     for (int v = 0; v < S.E; v++) {
-        int rc = copy_field(S.state[S.cur] + (size_t)v*S.g.fstride, q_cons[v], true, S.st);
+        int rc = copy_field(S.state[S.cur] + (size_t)v*S.g.fstride, q_cons[v], true, S.st, v);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(S.st));
@@ -624,7 +633,7 @@ int mfc_b200_upload(const double *const q_cons[]) {
 int mfc_b200_download(double *const q_cons[]) {
     if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_download before mfc_b200_upload");
     for (int v = 0; v < S.E; v++) {
-        int rc = copy_field(S.state[S.cur] + (size_t)v*S.g.fstride, q_cons[v], false, S.st);
+        int rc = copy_field(S.state[S.cur] + (size_t)v*S.g.fstride, q_cons[v], false, S.st, v);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(S.st));
@@ -641,7 +650,7 @@ int mfc_b200_download_prim(double *const q_prim[]) {
     for (int v = 0; v < S.E; v++) {
         const bool is_prim = v >= S.nf && v <= S.nf + S.nd;
         double *plane = is_prim ? S.prim + (size_t)(v - S.nf)*S.g.fstride : S.state[S.cur] + (size_t)v*S.g.fstride;
-        if ((rc = copy_field(plane, q_prim[v], false, S.st))) return rc;
+        if ((rc = copy_field(plane, q_prim[v], false, S.st, v))) return rc;
     }
     CK(cudaStreamSynchronize(S.st));
     return 0;
@@ -681,7 +690,7 @@ int mfc_b200_compute_rhs(const double *const q_cons[], double *const rhs[]) {
     double *scratch = S.state[(S.cur + 1) % 3];
     int rc;
     for (int v = 0; v < S.E; v++)
-        if ((rc = copy_field(scratch + (size_t)v*S.g.fstride, q_cons[v], true, S.st))) return rc;
+        if ((rc = copy_field(scratch + (size_t)v*S.g.fstride, q_cons[v], true, S.st, v))) return rc;
     if ((rc = rhs_stage(scratch, 0, scratch, scratch, 0.0, S.p.t_step_stop - 1, false, false))) return rc;
     const GridDesc &g = S.g;
     const size_t w = (size_t)(g.N[0] + 1)*sizeof(double);

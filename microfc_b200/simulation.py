@@ -120,8 +120,14 @@ class Simulation:
     def download(self, out_ghosted: Optional[np.ndarray] = None) -> np.ndarray:
         """p_main.fpp:296; returns this rank's interior cells."""
         buf = out_ghosted if out_ghosted is not None else np.empty((self.E,) + self.ghost_shape)
-        abi.check(self.L.mfc_b200_download(abi.field_pointers(list(buf))))
+        self.download_ghosted(buf)
         return np.ascontiguousarray(buf[self._interior()])
+
+    def download_ghosted(self, out_ghosted: np.ndarray) -> None:
+        """p_main.fpp:296 exactly: the device state lands in the host's own ghosted fields
+        sf(-b:m+b, ...) (no host-side repacking)."""
+        assert out_ghosted.shape == (self.E,) + self.ghost_shape and out_ghosted.dtype == np.float64
+        abi.check(self.L.mfc_b200_download(abi.field_pointers(list(out_ghosted))))
 
     def download_prim(self) -> np.ndarray:
         buf = np.empty((self.E,) + self.ghost_shape)
