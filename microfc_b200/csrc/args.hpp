@@ -45,6 +45,10 @@ struct SweepArgs {
     // q_cons_ts(1) seen as 4-D tensors (x, y, z, variable): one cp.async.bulk.tensor copy
     // brings a row of ALL variables into a ring slot, box = {kWX or kWY, 1, 1, E}
     TensorMap tm_q, tm_rhs, tm_q1;
+    // interior-clipped maps (cell indices as coordinates, extents N+1: out-of-range columns are
+    // zero-filled on load and dropped on store) of the RHS accumulator, q_cons_ts(1) and the
+    // destination of this sweep (RHS accumulator, or the updated state when rk_mode != 0)
+    TensorMap tm_rhs_i, tm_q1_i, tm_out_i;
     // viscous runs only (else nullptr): the sweep stores vel_src (nd planes) and Re_avg (2 planes)
     // of every face it solves, for k_visc (m_riemann_solvers.fpp:225-230,314-324)
     double *visc_face;

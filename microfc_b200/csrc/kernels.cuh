@@ -564,21 +564,26 @@ __device__ __forceinline__ void tma_load_row(void *dst, const TensorMap *tm, int
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(0), "r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_row(const TensorMap *tm, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(0) : "memory");
+// one row of all E variables, shared memory -> global (SASS UTMASTG); elements outside the tensor
+// (columns beyond the last interior cell of an interior-clipped map) are not written
+__device__ __forceinline__ void tma_store_row(const TensorMap *tm, int c0, int c1, int c2, const void *src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(0), "r"(smem_u32(src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// every bulk store committed by this thread has finished READING its shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy accesses to a slot must be ordered before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // tuning knobs (tools/tune_variants.py builds and times alternatives)
 #ifndef MFC_RING_Y
-#define MFC_RING_Y 6
+#define MFC_RING_Y 7
 #define MFC_WARPS_Y 4
-#define MFC_CTAS_Y 4
+#define MFC_CTAS_Y 3
 #endif
 #ifndef MFC_RING_Z
-#define MFC_RING_Z 8
+#define MFC_RING_Z 6
 #define MFC_CTAS_Z 3
 #endif
 #ifndef MFC_RING_X
@@ -592,22 +597,16 @@ constexpr int kWarpCells = 30; // cells finished per warp and row in the x kerne
 // doubles per ring slot: E rows of W doubles, padded so that every slot starts on a 128-byte line
 // (the TMA destination alignment)
 __host__ __device__ constexpr int slot_doubles(int E, int W) { return (E*W + 15)/16*16; }
-// Occupancy (measured at 512^3, profiles/r01_tune_occupancy.txt, r01_v3b_tune_pingpong_occupancy.txt):
-// x 5 CTAs x 4 warps (<= 96 registers, 40 KB of rings per CTA), y 4 CTAs x 4 warps (<= 128
-// registers, 6-slot rings), last direction (fused RK update, more live values) 3 CTAs x 4 warps
-// (<= 168 registers, 8-slot rings).
-#ifndef MFC_MARCH_PINGPONG
-// 1: two march iterations per loop trip with the carried face state in swapped register sets (no
-// copies, 6 % fewer instructions) -- measured SLOWER at 512^3 (y 7.9 vs 6.1 ms, z 11.1 vs 6.9 ms,
-// profiles/r01_v3b_tune_pingpong_occupancy.txt): the doubled loop body no longer fits the
-// instruction cache.  Kept for reference, off by default.
-#define MFC_MARCH_PINGPONG 0
-#endif
+// Occupancy (measured at 512^3, profiles/r01_tune_occupancy.txt, r01_v3b_tune_pingpong_occupancy.txt,
+// r01_v4_tune.txt): x 5 CTAs x 4 warps (<= 96 registers, 40 KB of rings per CTA); y and z 3 CTAs x
+// 4 warps (<= 168 registers, 72 KB per CTA: ring + the operand / output slots of k_march3).
 constexpr int kWarpsX = MFC_WARPS_X, kCtasX = MFC_CTAS_X;
 constexpr int kWarpsY = MFC_WARPS_Y, kCtasY = MFC_CTAS_Y;
 // the last direction carries the fused RK update (more live registers): its own occupancy knobs
 __host__ __device__ constexpr int march_ring(int dir, int nd) { return dir == nd - 1 ? MFC_RING_Z : kRingY; }
 __host__ __device__ constexpr int march_ctas(int dir, int nd) { return dir == nd - 1 ? MFC_CTAS_Z : kCtasY; }
+// ring + operand / output slots per warp of k_march3: ring | rhs in | q1 in (last direction) | out
+__host__ __device__ constexpr int march_slots(int dir, int nd) { return march_ring(dir, nd) + 2 + (dir == nd - 1 ? 1 : 0); }
 
 // cons -> prim of one cell held in a ring slot (stride LD between variables), in place:
 // momenta become velocities, the energy becomes the pressure (:187-227, :353-362, :98-106)
@@ -670,8 +669,6 @@ struct Weno {
     }
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // operands of finish_cell2 that stream from HBM, fetched ahead of the Riemann solve.
 // ACC: the RHS of earlier directions is accumulated (m_rhs.fpp:610-620); RK: this is the last
 // direction, the TVD-RK statement a.rk_mode (1..4, or 0 = store the RHS) is fused in.
@@ -711,29 +708,15 @@ __device__ __forceinline__ void load_cell(const SweepArgs &a, unsigned off, Cell
 #endif
     }
 }
-template <int NF, int ND, bool ACC, bool RK>
-__device__ __forceinline__ void prefetch_cell(const SweepArgs &a, unsigned off) {
-    constexpr int E = 2*NF + ND + 1;
-    if (ACC) {
-#pragma unroll
-        for (int v = 0; v < E; v++) prefetch_l2(a.rhs_v[v] + off);
-    }
-    if (RK) {
-        if (a.rk_mode >= 2) {
-#pragma unroll
-            for (int v = 0; v < E; v++) prefetch_l2(a.q1_v[v] + off);
-        }
-    }
-}
-
-// RHS of one cell + fused RK stage.  pc = the cell's entry in the ring (stride LD between
-// variables: partial densities and volume fractions as stored, velocities and pressure in
-// place of momenta and energy); in = the operands fetched by load_cell; store = false masks
-// the stores (lanes beyond the domain, halo lanes of the x kernel).
+// RHS of one cell + fused RK stage, returned in y[] (the RHS itself when !RK or rk_mode == 0,
+// else the updated state).  pc = the cell's entry in the ring (stride LD between variables:
+// partial densities and volume fractions as stored, velocities and pressure in place of momenta
+// and energy); in = the operands fetched by load_cell / from the operand slots.
 template <int NF, int ND, int LD, bool ACC, bool RK>
-__device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, bool store, double rds, const double *pc,
-                                             const CellIn<2*NF + ND + 1, ACC, RK> &in,
-                                             const double *Fm, double ufm, const double *Fp, double ufp) {
+__device__ __forceinline__ void finish_vals(const SweepArgs &a, double rds, const double *pc,
+                                            const CellIn<2*NF + ND + 1, ACC, RK> &in,
+                                            const double *Fm, double ufm, const double *Fp, double ufp,
+                                            double (&y)[2*NF + ND + 1]) {
     constexpr int E = 2*NF + ND + 1, MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
     double x[E], al[NF];
 #pragma unroll
@@ -755,19 +738,15 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
     }
 #endif
     if (!RK || a.rk_mode == 0) {
-        if (store) {
 #pragma unroll
-            for (int v = 0; v < E; v++) a.rhsw_v[v][off] = x[v];
-        }
+        for (int v = 0; v < E; v++) y[v] = x[v];
         return;
     }
 #if MFC_STRICT
-    if (store) {
 #pragma unroll
-        for (int v = 0; v < E; v++) {
-            const double qs = a.rk_mode >= 2 ? (v >= ADV ? al[v - ADV] : in.qs[v]) : 0.0;
-            a.qout_v[v][off] = rk_apply(a.rk_mode, in.q1[v], qs, x[v], a.dt);
-        }
+    for (int v = 0; v < E; v++) {
+        const double qs = a.rk_mode >= 2 ? (v >= ADV ? al[v - ADV] : in.qs[v]) : 0.0;
+        y[v] = rk_apply(a.rk_mode, in.q1[v], qs, x[v], a.dt);
     }
 #else
     // stage state rebuilt from the ring
@@ -792,19 +771,34 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
     // evaluated as k1 q1 + k2 qs + k3 rhs with the constants folded
     const int m = a.rk_mode;
     if (m == 1) {
-        if (store) {
 #pragma unroll
-            for (int v = 0; v < E; v++) a.qout_v[v][off] = fma(a.dt, x[v], qs[v]);
-        }
+        for (int v = 0; v < E; v++) y[v] = fma(a.dt, x[v], qs[v]);
     } else {
         const double c4 = m == 2 ? 0.5 : (m == 3 ? 0.25 : 1.0/3.0);
         const double k1 = (m == 3 ? 3.0 : 1.0)*c4, k2 = (m == 4 ? 2.0 : 1.0)*c4, k3 = (m == 4 ? 2.0 : 1.0)*a.dt*c4;
-        if (store) {
 #pragma unroll
-            for (int v = 0; v < E; v++) a.qout_v[v][off] = fma(k1, in.q1[v], fma(k2, qs[v], k3*x[v]));
-        }
+        for (int v = 0; v < E; v++) y[v] = fma(k1, in.q1[v], fma(k2, qs[v], k3*x[v]));
     }
 #endif
+}
+// the same with direct (masked) stores: store = false masks the stores (lanes beyond the domain,
+// halo lanes of the x kernel)
+template <int NF, int ND, int LD, bool ACC, bool RK>
+__device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, bool store, double rds, const double *pc,
+                                             const CellIn<2*NF + ND + 1, ACC, RK> &in,
+                                             const double *Fm, double ufm, const double *Fp, double ufp) {
+    constexpr int E = 2*NF + ND + 1;
+    double y[E];
+    finish_vals<NF, ND, LD, ACC, RK>(a, rds, pc, in, Fm, ufm, Fp, ufp, y);
+    if (store) {
+        if (!RK || a.rk_mode == 0) {
+#pragma unroll
+            for (int v = 0; v < E; v++) a.rhsw_v[v][off] = y[v];
+        } else {
+#pragma unroll
+            for (int v = 0; v < E; v++) a.qout_v[v][off] = y[v];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -932,62 +926,82 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// y / z sweep, v2.  Every WARP is an independent pipeline: it owns 32 consecutive x columns at
+// y / z sweep, v3.  Every WARP is an independent pipeline: it owns 32 consecutive x columns at
 // one transverse index and marches a pencil segment s0..s1 along the sweep direction.  Rows
-// s0-3 .. s1+3 stream through the warp's private ring (5 live rows of the stencil + the rows
-// in flight, one 256-byte bulk copy per variable and row); every lane converts, reads and
-// reconstructs only its own column, carrying the previous cell's right-face state and the
-// previous face's flux in registers, so the only synchronisation is a __syncwarp before a slot
-// is handed back to the TMA engine.  Lanes beyond the domain compute on whatever their ring
-// column holds and never store.
+// s0-3 .. s1+3 of the stage state stream through the warp's private ring (5 live rows of the
+// stencil + the rows in flight, one tensor-map bulk copy per row); every lane converts, reads
+// and reconstructs only its own column, carrying the previous cell's right-face state and the
+// previous face's flux in registers.  EVERY other HBM operand moves through the TMA engine too:
+//   rin   the RHS accumulated by the earlier directions (row of the cell being finished)
+//   qin   q_cons_ts(1) of that row (last direction, stages 2/3)
+//   outs  the finished row (RHS, or the updated state when the RK statement is fused in),
+//         written back with one bulk tensor store; the interior-clipped tensor map drops the
+//         columns beyond the domain, so there are no masked per-lane stores
+// Each operand row is requested one march iteration (~3 us) before it is read, so the warp
+// never waits on a global load (v3a: 8-11 % of all issue-stall samples sat on the first use of
+// an LDG'd operand, profiles/r01_v3a_stalls.md), and the 16 LDG/STG + 48 address instructions
+// per cell become 24 LDS/STS.  The only synchronisation is the mbarrier wait and a __syncwarp
+// before a slot is handed back.  Lanes beyond the domain compute on zero-filled columns.
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int DIR, int COEF, bool BC4, bool VISC, int WO>
-__global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march2(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
+__global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(const __grid_constant__ SweepArgs a) {
+    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
+    constexpr int NS = march_slots(DIR, ND);           // slots per warp: ring | rin | qin (RK) | outs
+    constexpr int NB = R + 2;                          // mbarriers per warp: ring slots, rin, qin
+    constexpr unsigned kRowBytes = (unsigned)(E*kWY*sizeof(double));
     static_assert(R >= 6, "the ring holds the 5 live rows of the stencil plus at least one row in flight");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsY*R*SLOT) + warp*R;
+    double *ring = reinterpret_cast<double *>(smem_raw) + warp*(NS*SLOT);
+    double *rin = ring + R*SLOT, *qin = rin + SLOT, *outs = ring + (NS - 1)*SLOT;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsY*NS*SLOT) + warp*NB;
+    unsigned long long *bar_r = bar + R, *bar_q = bar + R + 1;
     const int j0 = (blockIdx.x*kWarpsY + warp)*kWY;
-    if (j0 > g.N[0]) return;                           // whole warp out of range
+    if (j0 > g.N[0]) return;                           // whole warp out of range (no block barriers below)
     const bool on = j0 + lane <= g.N[0];
     const int t = blockIdx.z;
     const int s0 = blockIdx.y*a.seg;
     const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
     const long long ss = DIR == 1 ? g.sy : g.sz;
     const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the warp's columns
-    // rows s0-3 .. s1+3 (+1 when the ping-pong loop pads the iteration count to an even number)
-    const int r_first = s0 - 3, r_last = s1 + 3 + (MFC_MARCH_PINGPONG ? ((s1 - s0 + 3) & 1) : 0);
+    const int r_first = s0 - 3, r_last = s1 + 3;       // rows s0-3 .. s1+3
+    const bool need_q1 = RK && (MFC_STRICT ? a.rk_mode != 0 : a.rk_mode >= 2);
     if (lane == 0) {
-        for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
+        for (int i = 0; i < NB; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
-    // tensor coordinates of row r of the warp's columns: (x, y, z) in the padded box
+    // tensor coordinates of row r of the warp's columns: (x, y, z) in the padded box for the
+    // stage state; interior coordinates (cell indices) for the operand / output rows
     const int cx = j0 + kXoff, cy = (DIR == 1 ? 0 : t) + g.yoff, cz = (DIR == 1 ? t : 0) + g.zoff;
-    auto issue = [&](int r, int slot) {
-        mbar_expect_tx(&bar[slot], (unsigned)(E*kWY*sizeof(double)));
-        tma_load_row(ring + slot*SLOT, &a.tm_q, cx, DIR == 1 ? cy + r : cy, DIR == 1 ? cz : cz + r, &bar[slot]);
-    };
+    if (lane == 0) {
+        for (int r = r_first; r < r_first + R && r <= r_last; r++) {
+            mbar_expect_tx(&bar[r - r_first], kRowBytes);
+            tma_load_row(ring + (r - r_first)*SLOT, &a.tm_q, cx, DIR == 1 ? cy + r : cy, DIR == 1 ? cz : cz + r, &bar[r - r_first]);
+        }
+        // operands of the first cell finished (s0)
+        mbar_expect_tx(bar_r, kRowBytes);
+        tma_load_row(rin, &a.tm_rhs_i, j0, DIR == 1 ? s0 : t, DIR == 1 ? t : s0, bar_r);
+        if (need_q1) {
+            mbar_expect_tx(bar_q, kRowBytes);
+            tma_load_row(qin, &a.tm_q1_i, j0, DIR == 1 ? s0 : t, DIR == 1 ? t : s0, bar_q);
+        }
+    }
     int next_issue = r_first + R;                      // only lane 0 issues, every lane counts
-    if (lane == 0)
-        for (int r = r_first; r < r_first + R && r <= r_last; r++) issue(r, r - r_first);
 
     // ring bookkeeping (R need not be a power of two): slot / phase of the next row to wait for
     // and convert, slot of row s-2 (the one handed back at the end of the iteration), and the
     // lane's pointers to rows s-2 .. s+2
     int slot_cv = 0, slot_lo = 0;
-    unsigned phase_cv = 0;
-    auto convert_next = [&]() {
+    unsigned phase_cv = 0, phase_op = 0;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {                      // rows s0-3 .. s0
         mbar_wait(&bar[slot_cv], phase_cv);
         prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
         if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
-    };
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) convert_next();        // rows s0-3 .. s0
+    }
     const double *p0 = ring + lane, *p1 = p0 + SLOT, *p2 = p1 + SLOT, *p3 = p2 + SLOT, *p4 = p3 + SLOT;
     const double *const ring_end = ring + R*SLOT;
 
@@ -995,33 +1009,52 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march2(cons
     // plane-relative element offset of cell s-1 of my column (lanes beyond the domain: column N)
     unsigned off = (unsigned)(base + (min(j0 + lane, g.N[0]) - j0) + (long long)(s0 - 3)*ss);
     Weno<COEF, WO> weno;
-    // One iteration of the march: reconstruct cell s, solve face s-1/2 against the right-face
-    // state carried from cell s-1 (vRi), finish cell s-1 with the flux carried from face s-3/2
-    // (Fi, ufi).  The carried values go OUT in different registers (vRo, Fo, ufo): the loop below
-    // calls the body twice with the two sets swapped, so nothing is copied between iterations.
-    auto body = [&](const int s, const bool real, const double (&vRi)[E], const double (&Fi)[E], const double ufi,
-                    double (&vRo)[E], double (&Fo)[E], double &ufo) {
-        convert_next();                                // row s+2
+    // carried from cell s-1 / face s-3/2: right-face state, flux, face velocity
+    double vRp[E], Fp[E], ufp = 0.0;
+#pragma unroll
+    for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
+    // One iteration of the march: reconstruct cell s, solve face s-1/2 against the carried
+    // right-face state of cell s-1, finish cell s-1 with the carried flux of face s-3/2.
+#pragma unroll 1
+    for (int s = s0 - 1; s <= s1 + 1; s++) {
+        mbar_wait(&bar[slot_cv], phase_cv);            // row s+2
+        prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
+        if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
         off += uss;
-        const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
-        if (lane == 0 && s <= s1) {                    // operands of the NEXT iteration's finish -> L2
-            tma_prefetch_row(&a.tm_rhs, cx, DIR == 1 ? cy + s : cy, DIR == 1 ? cz : cz + s);
-            if (RK && a.rk_mode >= (MFC_STRICT ? 1 : 2)) tma_prefetch_row(&a.tm_q1, cx, DIR == 1 ? cy + s : cy, DIR == 1 ? cz : cz + s);
-        }
         weno.load(a, s);
-        double vL[E];
+        double vL[E], vRn[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
             const double st[5] = {p0[v*kWY], p1[v*kWY], p2[v*kWY], p3[v*kWY], p4[v*kWY]};
-            weno(st, vL[v], vRo[v]);
+            weno(st, vL[v], vRn[v]);
         }
+        const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
         if (s >= s0) {
+            double Fn[E], ufn;
             CellIn<E, ACC, RK> in;
-            if (fin) load_cell<NF, ND, ACC, RK>(a, off, in);
+            if (fin) {                                 // operand rows requested one iteration ago
+                mbar_wait(bar_r, phase_op);
+#pragma unroll
+                for (int v = 0; v < E; v++) in.r[v] = rin[v*kWY + lane];
+                if (RK) {
+                    if (need_q1) {
+                        mbar_wait(bar_q, phase_op);
+#pragma unroll
+                        for (int v = 0; v < E; v++) in.q1[v] = qin[v*kWY + lane];
+                    }
+#if MFC_STRICT
+                    if (a.rk_mode >= 2) {
+#pragma unroll
+                        for (int v = 0; v < ADV; v++) in.qs[v] = __ldg(a.q_v[v] + off);
+                    }
+#endif
+                }
+                phase_op ^= 1u;
+            }
             double Ls[BC4 ? E : 1];
             if (BC4) {
 #pragma unroll
-                for (int v = 0; v < E; v++) Ls[v] = vRi[v];
+                for (int v = 0; v < E; v++) Ls[v] = vRp[v];
                 if (a.bc_beg == -4 && s == 0) {
 #pragma unroll
                     for (int v = 0; v < E; v++) Ls[v] = vL[v];
@@ -1031,43 +1064,53 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march2(cons
                     for (int v = 0; v < E; v++) vL[v] = Ls[v];
                 }
             }
-            const double *L = BC4 ? Ls : vRi;
+            const double *L = BC4 ? Ls : vRp;
             double vs[ND];
-            hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Fo, ufo, vs);
-            if (VISC && on && real) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
-            if (fin) finish_cell2<NF, ND, kWY, ACC, RK>(a, off, on && real, a.rds[s - 1 + g.b], p1, in, Fi, ufi, Fo, ufo);   // p1: row s-1
+            hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Fn, ufn, vs);
+            if (VISC && on) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
+            if (fin) {
+                double y[E];
+                finish_vals<NF, ND, kWY, ACC, RK>(a, a.rds[s - 1 + g.b], p1, in, Fp, ufp, Fn, ufn, y);   // p1: row s-1
+                if (lane == 0) tma_store_wait_read();  // the previous row has left the output slot
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < E; v++) outs[v*kWY + lane] = y[v];
+            }
+#pragma unroll
+            for (int v = 0; v < E; v++) Fp[v] = Fn[v];
+            ufp = ufn;
         }
+        // One proxy fence per iteration orders, for the whole warp, (a) the output row written
+        // above before the bulk store reads it, (b) the reads of the operand slots and of ring
+        // row s-2 before the TMA engine overwrites them.
         fence_proxy_async();
-        __syncwarp();                                  // row s-2 is dead for the whole warp
-        if (next_issue <= r_last) {
-            if (lane == 0) issue(next_issue, slot_lo);
-            next_issue++;
+        __syncwarp();
+        if (lane == 0) {
+            if (fin) {
+                tma_store_row(&a.tm_out_i, j0, DIR == 1 ? s - 1 : t, DIR == 1 ? t : s - 1, outs);
+                if (s <= s1) {                         // operands of cell s, finished by the next iteration
+                    mbar_expect_tx(bar_r, kRowBytes);
+                    tma_load_row(rin, &a.tm_rhs_i, j0, DIR == 1 ? s : t, DIR == 1 ? t : s, bar_r);
+                    if (need_q1) {
+                        mbar_expect_tx(bar_q, kRowBytes);
+                        tma_load_row(qin, &a.tm_q1_i, j0, DIR == 1 ? s : t, DIR == 1 ? t : s, bar_q);
+                    }
+                }
+            }
+            if (next_issue <= r_last) {
+                mbar_expect_tx(&bar[slot_lo], kRowBytes);
+                tma_load_row(ring + slot_lo*SLOT, &a.tm_q, cx, DIR == 1 ? cy + next_issue : cy, DIR == 1 ? cz : cz + next_issue, &bar[slot_lo]);
+            }
         }
+        next_issue++;
         if (++slot_lo == R) slot_lo = 0;
         p0 = p1; p1 = p2; p2 = p3; p3 = p4;
         p4 += SLOT;
         if (p4 >= ring_end) p4 -= R*SLOT;
-    };
-    double vRa[E], Fa[E], ufa = 0.0, vRb[E], Fb[E], ufb = 0.0;
 #pragma unroll
-    for (int v = 0; v < E; v++) { vRa[v] = 0.0; Fa[v] = 0.0; vRb[v] = 0.0; Fb[v] = 0.0; }
-#if MFC_MARCH_PINGPONG
-    // iterations s0-1 .. s1+1, padded to an even count with one masked iteration (its extra row
-    // s1+4 is at most the outermost ghost row, b >= 4)
-#pragma unroll 1
-    for (int s = s0 - 1; s <= s1 + 1; s += 2) {
-        body(s, true, vRa, Fa, ufa, vRb, Fb, ufb);
-        body(s + 1, s + 1 <= s1 + 1, vRb, Fb, ufb, vRa, Fa, ufa);
+        for (int v = 0; v < E; v++) vRp[v] = vRn[v];
     }
-#else
-#pragma unroll 1
-    for (int s = s0 - 1; s <= s1 + 1; s++) {
-        body(s, true, vRa, Fa, ufa, vRb, Fb, ufb);
-#pragma unroll
-        for (int v = 0; v < E; v++) { vRa[v] = vRb[v]; Fa[v] = Fb[v]; }
-        ufa = ufb;
-    }
-#endif
+    if (lane == 0) tma_store_wait_read();              // the output slot must outlive the last store's read
 }
 
 // ------------------------------------------------------------------------------------------

@@ -77,8 +77,9 @@ struct Sim {
     const double *last_q = nullptr;    // state of the most recent RHS evaluation (what q_prim_vf reflects)
     double *prim = nullptr, *rhs = nullptr, *snap = nullptr;
     // TMA descriptors of the three state buffers and the RHS accumulator, [0]: box kWX wide (x
-    // sweep), [1]: box kWY wide (y/z march)
-    TensorMap tm_state[3][2], tm_rhs[2];
+    // sweep), [1]: box kWY wide (y/z march), [2]: interior cells only, box kWY wide (operand loads
+    // and output stores of the march)
+    TensorMap tm_state[3][3], tm_rhs[3];
     double *coef[3] = {nullptr, nullptr, nullptr};
     int clen[3] = {0, 0, 0}, coef_lo[3] = {0, 0, 0};
     int coef_uniform[3] = {0, 0, 0};   // every cell of the direction has the same 27 coefficients (to 1e-12)
@@ -177,7 +178,9 @@ size_t field_bytes() { return (size_t)S.g.fstride*sizeof(double); }
 
 // E padded planes seen as the 4-D tensor (x, y, z, variable); box = one row of boxw columns of
 // every variable, which lands in shared memory as E consecutive runs of boxw doubles
-int make_tmap(TensorMap &out, double *base, int boxw) {
+// interior = true: only the interior cells (coordinates = cell indices, extents N+1), so that a box
+// hanging over the last interior column is zero-filled on load and clipped on store
+int make_tmap(TensorMap &out, double *base, int boxw, bool interior = false) {
     typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -190,7 +193,11 @@ int make_tmap(TensorMap &out, double *base, int boxw) {
         encode = (Encode)fn;
     }
     const GridDesc &g = S.g;
-    const cuuint64_t dims[4] = {(cuuint64_t)g.pitch, (cuuint64_t)g.ey, (cuuint64_t)g.ez, (cuuint64_t)S.E};
+    cuuint64_t dims[4] = {(cuuint64_t)g.pitch, (cuuint64_t)g.ey, (cuuint64_t)g.ez, (cuuint64_t)S.E};
+    if (interior) {
+        base += g.at(0, 0, 0);                           // 128-byte aligned: kXoff and the pitch are multiples of 16 doubles
+        dims[0] = (cuuint64_t)g.N[0] + 1; dims[1] = (cuuint64_t)g.N[1] + 1; dims[2] = (cuuint64_t)g.N[2] + 1;
+    }
     const cuuint64_t strides[3] = {(cuuint64_t)g.sy*8, (cuuint64_t)g.sz*8, (cuuint64_t)g.fstride*8};
     const cuuint32_t box[4] = {(cuuint32_t)boxw, 1, 1, (cuuint32_t)S.E};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -401,6 +408,10 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
             const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
             if (!tq || !t1) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
             a.tm_q = *tq; a.tm_q1 = *t1; a.tm_rhs = S.tm_rhs[d == 0 ? 0 : 1];
+            // interior-clipped maps of the march kernels' operand rows and of this sweep's destination
+            const TensorMap *t1i = state_tmap(q1, 2), *toi = a.rk_mode != 0 ? state_tmap(qout, 2) : &S.tm_rhs[2];
+            if (!t1i || !toi) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
+            a.tm_rhs_i = S.tm_rhs[2]; a.tm_q1_i = *t1i; a.tm_out_i = *toi;
         }
         Scope sc(KC_SWEEP_X + d);
         const int n = S.L->sweep(S.nf, S.nd, d, a, S.st);
@@ -441,21 +452,33 @@ int do_step(int t_step, double dt, bool stab) {
 
 // host field (Fortran sf(-b:m+b, ...), x fastest, contiguous) <-> padded device plane.  The
 // host array crosses PCIe as ONE contiguous copy into a staging plane (the RHS accumulator, which
-// is scratch between steps) and is re-pitched on the device; a strided 2-D copy of 4 KB rows
-// straight from host memory reaches only ~8 GB/s.
+// is scratch between steps) and is re-pitched by a kernel: a strided 2-D copy of 4 KB rows
+// straight from host memory reaches only ~8 GB/s, and the copy engine's device-to-device 2-D copy
+// of 270 k short rows is no faster (~10 GB/s end to end, measured); the kernel runs at HBM speed,
+// so the transfer is bound by the PCIe link (~55 GB/s measured with pinned host memory).
+__global__ void __launch_bounds__(256) k_repitch(double *pitched, double *packed, int w, int pitch, bool to_pitched) {
+    const size_t r = blockIdx.x;
+    double *p = pitched + r*(size_t)pitch, *c = packed + r*(size_t)w;
+    for (int j = threadIdx.x; j < w; j += 256) {
+        if (to_pitched) p[j] = c[j];
+        else c[j] = p[j];
+    }
+}
 int copy_field(double *dev_plane, const double *host, bool to_device, cudaStream_t st, int v) {
     const GridDesc &g = S.g;
-    const size_t w = (size_t)(g.N[0] + 1 + 2*g.b)*sizeof(double);
+    const int wd = g.N[0] + 1 + 2*g.b;
+    const size_t w = (size_t)wd*sizeof(double);
     double *d0 = dev_plane + (kXoff - g.b);
     const size_t rows = (size_t)g.ey*g.ez;
     double *stage = S.rhs + (size_t)v*g.fstride;         // w*rows <= fstride*8 bytes
     if (to_device) {
         CK(cudaMemcpyAsync(stage, host, w*rows, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpy2DAsync(d0, (size_t)g.pitch*sizeof(double), stage, w, w, rows, cudaMemcpyDeviceToDevice, st));
+        k_repitch<<<(unsigned)rows, 256, 0, st>>>(d0, stage, wd, g.pitch, true);
     } else {
-        CK(cudaMemcpy2DAsync(stage, w, d0, (size_t)g.pitch*sizeof(double), w, rows, cudaMemcpyDeviceToDevice, st));
+        k_repitch<<<(unsigned)rows, 256, 0, st>>>(d0, stage, wd, g.pitch, false);
         CK(cudaMemcpyAsync(const_cast<double *>(host), stage, w*rows, cudaMemcpyDeviceToHost, st));
     }
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -543,6 +566,12 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         for (int i = 0; i < 3; i++)
             if ((rc = make_tmap(S.tm_state[i][w], S.state[i], w == 0 ? kWX : kWY))) return rc;
         if ((rc = make_tmap(S.tm_rhs[w], S.rhs, w == 0 ? kWX : kWY))) return rc;
+    }
+    {
+        int rc;
+        for (int i = 0; i < 3; i++)
+            if ((rc = make_tmap(S.tm_state[i][2], S.state[i], kWY, true))) return rc;
+        if ((rc = make_tmap(S.tm_rhs[2], S.rhs, kWY, true))) return rc;
     }
     if (visc) {
         CK(cudaMalloc(&S.visc_face, field_bytes()*(nd + 2))); CK(cudaMemsetAsync(S.visc_face, 0, field_bytes()*(nd + 2), S.st));

@@ -14,10 +14,10 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     # name: (RING_Y, WARPS_Y, CTAS_Y, RING_X, WARPS_X, CTAS_X, extra -D flags)
-    "pp_z4": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_PINGPONG=1"),
-    "pp_z3r8": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_PINGPONG=1 -DMFC_RING_Z=8 -DMFC_CTAS_Z=3"),
-    "nopp_z3r8": (6, 4, 4, 4, 4, 5, "-DMFC_MARCH_PINGPONG=0 -DMFC_RING_Z=8 -DMFC_CTAS_Z=3"),
-    "pp_y3z3r8": (8, 4, 3, 4, 4, 5, "-DMFC_MARCH_PINGPONG=1 -DMFC_RING_Z=8 -DMFC_CTAS_Z=3"),
+    "base": (6, 4, 4, 4, 4, 5, ""),
+    "y3r8": (8, 4, 3, 4, 4, 5, ""),
+    "y3r7_x4": (7, 4, 3, 4, 4, 4, ""),
+    "y4_z2r10": (6, 4, 4, 4, 4, 5, "-DMFC_RING_Z=10 -DMFC_CTAS_Z=2"),
 }
 
 
