@@ -226,23 +226,13 @@ def main():
     cb = pre_process.generate_grid(cfg)
     sim = Simulation(cfg, cb, rank=rank, num_procs=world, device=local_rank, broadcast_id=bcast_id if world > 1 else None)
     lay = sim.layout
-    # initial condition of this rank, generated in z-slabs straight into the (pinned) host
-    # buffer the Fortran host would own: sf(-b:m+b, -b:n+b, -b:p+b) per variable
+    # initial condition of this rank: laid out on the device from the case's patches
+    # (mfc_b200_generate_initial_condition) and brought back once into the (pinned)
+    # host buffer the Fortran host would own, sf(-b:m+b, -b:n+b, -b:p+b) per variable, so that
+    # the end-to-end leg below starts from HOST data
     host = torch.empty((E,) + sim.ghost_shape, dtype=torch.float64, pin_memory=True).numpy()
-    host[...] = 0.0
-    zs, ys, xs = lay.interior_slices()
-    b = sim.b
-    chunk = 32 if nd == 3 else (lay.N[1] + 1)
-    oz = b if nd > 2 else 0
-    oy = b if nd > 1 else 0
-    if nd == 3:
-        for z0 in range(zs.start, zs.stop, chunk):
-            z1 = min(z0 + chunk, zs.stop)
-            q = pre_process.generate_initial_condition(cfg, cb, box=(slice(z0, z1), ys, xs))
-            host[:, oz + z0 - zs.start:oz + z1 - zs.start, oy:oy + lay.N[1] + 1, b:b + lay.N[0] + 1] = q
-    else:
-        q = pre_process.generate_initial_condition(cfg, cb, box=(zs, ys, xs))
-        host[:, oz:oz + lay.N[2] + 1, oy:oy + lay.N[1] + 1, b:b + lay.N[0] + 1] = q
+    sim.generate_initial_condition(cb)
+    sim.download_ghosted(host)
     sim.upload_ghosted(host)
     sim.snapshot()
     dt = cfg.dt

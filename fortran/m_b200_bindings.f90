@@ -24,10 +24,32 @@ module m_b200_bindings
     private
     public :: mfc_b200_params_t, &
               s_b200_initialize, s_b200_upload, s_b200_time_step, &
-              s_b200_download, s_b200_download_prim, s_b200_compute_rhs, s_b200_finalize
+              s_b200_download, s_b200_download_prim, s_b200_compute_rhs, s_b200_finalize, &
+              mfc_b200_patch_t, s_b200_generate_initial_condition
 
     integer(c_int), parameter :: MFC_B200_MAX_FLUIDS = 4
     integer(c_int), parameter :: MFC_B200_ABI_VERSION = 1
+    integer(c_int), parameter :: MFC_B200_MAX_PATCHES = 10
+
+    !> mfc_b200_patch_t (include/mfc_b200.h): patch_icpp(i) as pre_process holds it
+    !! (ic_patch_parameters, src/common/m_derived_types.f90:55-103)
+    type, bind(C) :: mfc_b200_patch_t
+        integer(c_int32_t) :: geometry
+        integer(c_int32_t) :: smoothen
+        integer(c_int32_t) :: smooth_patch_id
+        integer(c_int32_t) :: alter_patch(0:MFC_B200_MAX_PATCHES)
+        real(c_double)     :: x_centroid, y_centroid, z_centroid
+        real(c_double)     :: length_x, length_y, length_z
+        real(c_double)     :: radius
+        real(c_double)     :: radii(3)
+        real(c_double)     :: normal(3)
+        real(c_double)     :: epsilon
+        real(c_double)     :: smooth_coeff
+        real(c_double)     :: vel(3)
+        real(c_double)     :: pres
+        real(c_double)     :: alpha_rho(MFC_B200_MAX_FLUIDS)
+        real(c_double)     :: alpha(MFC_B200_MAX_FLUIDS)
+    end type mfc_b200_patch_t
 
     !> mfc_b200_params_t (include/mfc_b200.h): everything the hot path reads from module
     !! globals in the reference (m_global_parameters.fpp:32-215), after decomposition.
@@ -114,6 +136,16 @@ module m_b200_bindings
             type(c_ptr), intent(in) :: q_cons(*), rhs(*)
             integer(c_int) :: ierr
         end function mfc_b200_compute_rhs
+
+        function mfc_b200_generate_initial_condition(num_patches, patches, cc, ds_min) &
+            bind(C, name='mfc_b200_generate_initial_condition') result(ierr)
+            import :: c_int, c_int32_t, c_ptr, c_double, mfc_b200_patch_t
+            integer(c_int32_t), value :: num_patches
+            type(mfc_b200_patch_t), intent(in) :: patches(*)
+            type(c_ptr), intent(in) :: cc(3)
+            real(c_double), value :: ds_min
+            integer(c_int) :: ierr
+        end function mfc_b200_generate_initial_condition
 
         function mfc_b200_download(q_cons) bind(C, name='mfc_b200_download') result(ierr)
             import :: c_int, c_ptr
@@ -277,6 +309,47 @@ contains
             time_avg = 0d0
         end if
     end subroutine s_b200_time_step
+
+    !> The pre_process stage on the device (SURVEY 8f-2): lays patch_icpp(1:num_patches) over this
+    !! rank's cells exactly like s_generate_initial_condition (src/pre_process/
+    !! m_initial_condition.fpp:42-113) and leaves the conservative state in HBM, replacing the
+    !! restart-file round trip + s_b200_upload.  x_cc_pre/y_cc_pre: pre_process' cell centres
+    !! (x_cb(i-1) + x_cb(i))/2 of the local cells (m_start_up.fpp:717,743); ds_min: the global
+    !! minimum cell width (s_mpi_reduce_min, :720).
+    subroutine s_b200_generate_initial_condition(patch_icpp, num_patches, x_cc_pre, y_cc_pre, ds_min)
+        use m_derived_types
+        type(ic_patch_parameters), intent(in) :: patch_icpp(:)
+        integer, intent(in) :: num_patches
+        real(kind(0d0)), intent(in), target :: x_cc_pre(0:), y_cc_pre(0:)
+        real(kind(0d0)), intent(in) :: ds_min
+        type(mfc_b200_patch_t) :: c(num_patches)
+        type(c_ptr) :: cc(3)
+        integer :: i, k
+        do i = 1, num_patches
+            c(i)%geometry = patch_icpp(i)%geometry
+            c(i)%smoothen = merge(1, 0, patch_icpp(i)%smoothen)
+            c(i)%smooth_patch_id = patch_icpp(i)%smooth_patch_id
+            c(i)%alter_patch = 0
+            do k = 0, num_patches
+                c(i)%alter_patch(k) = merge(1, 0, patch_icpp(i)%alter_patch(k))
+            end do
+            c(i)%x_centroid = patch_icpp(i)%x_centroid; c(i)%y_centroid = patch_icpp(i)%y_centroid
+            c(i)%z_centroid = patch_icpp(i)%z_centroid
+            c(i)%length_x = patch_icpp(i)%length_x; c(i)%length_y = patch_icpp(i)%length_y; c(i)%length_z = 0d0
+            c(i)%radius = patch_icpp(i)%radius
+            c(i)%radii = 0d0; c(i)%radii(1:2) = patch_icpp(i)%radii
+            c(i)%normal = 0d0; c(i)%normal(1:2) = patch_icpp(i)%normal
+            c(i)%epsilon = patch_icpp(i)%epsilon
+            c(i)%smooth_coeff = patch_icpp(i)%smooth_coeff
+            c(i)%vel = 0d0; c(i)%vel(1:2) = patch_icpp(i)%vel
+            c(i)%pres = patch_icpp(i)%pres
+            c(i)%alpha_rho = patch_icpp(i)%alpha_rho(1:MFC_B200_MAX_FLUIDS)
+            c(i)%alpha = patch_icpp(i)%alpha(1:MFC_B200_MAX_FLUIDS)
+        end do
+        cc(1) = c_loc(x_cc_pre); cc(2) = c_loc(y_cc_pre); cc(3) = c_null_ptr
+        call s_b200_check(mfc_b200_generate_initial_condition(int(num_patches, c_int32_t), c, cc, ds_min), &
+                          'mfc_b200_generate_initial_condition')
+    end subroutine s_b200_generate_initial_condition
 
     !> p_main.fpp:218,296 and m_time_steppers.fpp:374 -- "!$acc update host(...)"
     subroutine s_b200_download(q_cons_vf)

@@ -146,6 +146,44 @@ int mfc_b200_compute_rhs(const double *const q_cons[], double *const rhs[]);
 int mfc_b200_download(double *const q_cons[/*sys_size*/]);
 int mfc_b200_download_prim(double *const q_prim[/*sys_size*/]);
 
+/* ---- initial condition on the device -------------------------------------
+   The reference's pre_process executable lays patch_icpp(1..num_patches) over the grid
+   (src/pre_process/m_initial_condition.fpp:42-113, m_create_patches.fpp, m_assign_patches.fpp:
+   54-165), converts to conservative variables (src/common/m_variables_conversion.fpp:385-443)
+   and writes restart files that the simulation reads back and uploads.  This entry does the
+   same on the device, straight into the library's state, and replaces that file round trip +
+   mfc_b200_upload for hosts that start from patches: 512^3 x 8 variables per GPU never exist on
+   the host.  Fields mirror patch_icpp (src/pre_process/m_global_parameters.fpp:196-230).
+   Geometries: 1 line segment, 2 circle, 3 rectangle, 4 sweep line, 5 ellipse, 18 varcircle;
+   8 sphere, 9 cuboid, 10 z-invariant cylinder are the 3-D extension.  Anything else fails with
+   MFC_B200_EUNSUPPORTED. */
+#define MFC_B200_MAX_PATCHES 10   /* num_patches_max */
+typedef struct mfc_b200_patch {
+    int32_t geometry;
+    int32_t smoothen;          /* logical */
+    int32_t smooth_patch_id;   /* 1-based id of the patch this one is smeared against */
+    int32_t alter_patch[MFC_B200_MAX_PATCHES + 1];   /* alter_patch(0:num_patches), logical */
+    double x_centroid, y_centroid, z_centroid;
+    double length_x, length_y, length_z;
+    double radius;
+    double radii[3];
+    double normal[3];
+    double epsilon;
+    double smooth_coeff;
+    double vel[3];
+    double pres;
+    double alpha_rho[MFC_B200_MAX_FLUIDS];
+    double alpha[MFC_B200_MAX_FLUIDS];
+} mfc_b200_patch_t;
+
+/* cc[d]: pre_process' cell centres (x_cb(i-1) + x_cb(i))/2 (m_start_up.fpp:717,743) of THIS
+   rank's interior cells, N_d + 1 doubles per active direction; ds_min: the smallest cell width
+   of the GLOBAL grid over all active directions (the smoothing length scale,
+   m_create_patches.fpp:123).  Must follow mfc_b200_init; leaves the library in the same state
+   as mfc_b200_upload of the generated fields. */
+int mfc_b200_generate_initial_condition(int32_t num_patches, const mfc_b200_patch_t *patches,
+                                        const double *const cc[3], double ds_min);
+
 /* p_main.fpp:329-341 -- module finalisers. */
 int mfc_b200_finalize(void);
 

@@ -42,6 +42,23 @@ class Params(C.Structure):
     ]
 
 
+MAX_PATCHES = 10
+
+
+class Patch(C.Structure):
+    """mfc_b200_patch_t (patch_icpp(i), src/pre_process/m_global_parameters.fpp:196-230)"""
+    _fields_ = [
+        ("geometry", C.c_int32), ("smoothen", C.c_int32), ("smooth_patch_id", C.c_int32),
+        ("alter_patch", C.c_int32 * (MAX_PATCHES + 1)),
+        ("x_centroid", C.c_double), ("y_centroid", C.c_double), ("z_centroid", C.c_double),
+        ("length_x", C.c_double), ("length_y", C.c_double), ("length_z", C.c_double),
+        ("radius", C.c_double), ("radii", C.c_double * 3), ("normal", C.c_double * 3),
+        ("epsilon", C.c_double), ("smooth_coeff", C.c_double),
+        ("vel", C.c_double * 3), ("pres", C.c_double),
+        ("alpha_rho", C.c_double * MAX_FLUIDS), ("alpha", C.c_double * MAX_FLUIDS),
+    ]
+
+
 class MfcB200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmfc_b200: {msg} (code {code})")
@@ -79,6 +96,7 @@ def lib() -> C.CDLL:
     L.mfc_b200_sync.argtypes = []
     L.mfc_b200_compute_rhs.argtypes = [pp, pp]
     L.mfc_b200_download.argtypes = [pp]
+    L.mfc_b200_generate_initial_condition.argtypes = [C.c_int32, C.POINTER(Patch), pp, C.c_double]
     L.mfc_b200_download_prim.argtypes = [pp]
     L.mfc_b200_finalize.argtypes = []
     L.mfc_b200_last_error.restype = C.c_char_p
@@ -108,4 +126,5 @@ EXPORTED_SYMBOLS = [
     "mfc_b200_download", "mfc_b200_download_prim", "mfc_b200_finalize", "mfc_b200_last_error",
     "mfc_b200_get_weno_coefficients", "mfc_b200_kernel_launches", "mfc_b200_state_snapshot",
     "mfc_b200_state_restore", "mfc_b200_timer_start", "mfc_b200_timer_stop", "mfc_b200_profile_enable", "mfc_b200_profile_get", "mfc_b200_kernel_name",
+    "mfc_b200_generate_initial_condition",
 ]

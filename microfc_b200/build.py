@@ -31,6 +31,7 @@ UNITS = [
     ("kernels_strict.cu", ["-fmad=false"]),
     ("mfc_api.cu", ["-Xcompiler", "-fvisibility=default"]),
     ("weno_coefficients.cpp", ["-Xcompiler", "-ffp-contract=off"]),
+    ("patches.cu", ["-fmad=false"]),
 ]
 
 

@@ -115,6 +115,27 @@ struct StabArgs {
     unsigned long long *out;   // [0] icfl max, [1] vcfl max, [2] Rc min  as ordered bit patterns
 };
 
+// initial condition on the device (patches.cu): patch_icpp(i) as pre_process reads it
+// (src/pre_process/m_global_parameters.fpp:196-230); layout = mfc_b200_patch_t of the C ABI
+constexpr int kMaxPatches = 10;    // num_patches_max, src/pre_process/m_global_parameters.fpp
+struct PatchDesc {
+    int geometry, smoothen, smooth_patch_id;
+    int alter_patch[kMaxPatches + 1];
+    double x_centroid, y_centroid, z_centroid, length_x, length_y, length_z, radius;
+    double radii[3], normal[3], epsilon, smooth_coeff;
+    double vel[3], pres, alpha_rho[kMaxFluids], alpha[kMaxFluids];
+};
+struct PatchArgs {
+    GridDesc g;
+    double *q;                 // state planes (conservative variables are written to the interior)
+    const double *cc[3];       // pre_process cell centres of this rank's interior cells, N_d + 1 doubles
+    const PatchDesc *patches;  // device copy, num_patches entries in patch order
+    int num_patches;
+    double ds_min;             // min(dx, dy[, dz]) over the GLOBAL grid (s_mpi_reduce_min, m_start_up.fpp:720)
+    double gammas[kMaxFluids], pi_infs[kMaxFluids];
+};
+int launch_patches(int nf, int nd, const PatchArgs &a, cudaStream_t st);
+
 // number of (transverse x layer) elements of one variable in a ghost slab of direction dir:
 // earlier directions ghosted, later ones interior only (m_rhs.fpp:696-697 vs :811-812)
 MFC_HD long long slab_count(const GridDesc &g, int dir) {

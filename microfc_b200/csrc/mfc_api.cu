@@ -25,9 +25,9 @@ using namespace mfc;
 
 namespace {
 
-enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_RK, KC_COUNT };
+enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_RK, KC_PATCH, KC_COUNT };
 const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_sweep_x", "k_sweep_march<y>", "k_sweep_march<z>",
-                                      "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_rk"};
+                                      "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_rk", "k_patches"};
 
 // NCCL is resolved at run time so the library loads (and every symbol is exported) on hosts
 // without it; only mfc_b200_comm_init needs it.  In a process that already imported torch
@@ -655,6 +655,56 @@ int mfc_b200_upload(const double *const q_cons[]) {
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(S.st));
+    S.uploaded = true;
+    return 0;
+}
+
+int mfc_b200_generate_initial_condition(int32_t num_patches, const mfc_b200_patch_t *patches,
+                                        const double *const cc[3], double ds_min) {
+    if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_generate_initial_condition before mfc_b200_init");
+    if (num_patches < 1 || num_patches > MFC_B200_MAX_PATCHES || !patches || !cc)
+        return fail(MFC_B200_EINVAL, "num_patches must be 1..MFC_B200_MAX_PATCHES with non-NULL arrays");
+    static_assert(sizeof(PatchDesc) == sizeof(mfc_b200_patch_t), "PatchDesc mirrors mfc_b200_patch_t");
+    for (int i = 0; i < num_patches; i++) {
+        const int geo = patches[i].geometry;
+        const bool ok = geo == 1 || ((geo == 2 || geo == 3 || geo == 4 || geo == 5 || geo == 18) && S.nd >= 2) ||
+                        ((geo == 8 || geo == 9 || geo == 10) && S.nd == 3);
+        if (!ok) return fail(MFC_B200_EUNSUPPORTED, "patch geometry " + std::to_string(geo) + " is not built for this num_dims");
+        if (patches[i].smooth_patch_id < 0 || patches[i].smooth_patch_id > num_patches)
+            return fail(MFC_B200_EINVAL, "smooth_patch_id out of range");
+    }
+    const GridDesc &g = S.g;
+    PatchArgs a{};
+    a.g = g; a.q = S.state[S.cur]; a.num_patches = num_patches; a.ds_min = ds_min;
+    for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
+    // scratch for the cell centres and the patch table: the RHS accumulator (idle between steps)
+    double *scr = S.rhs;
+    size_t used = 0;
+    for (int d = 0; d < S.nd; d++) {
+        if (!cc[d]) return fail(MFC_B200_EINVAL, "cc[d] is NULL for an active direction");
+        used += ((size_t)g.N[d] + 1 + 15)/16*16;
+    }
+    if (used*sizeof(double) + (size_t)num_patches*sizeof(PatchDesc) > field_bytes()*S.E)
+        return fail(MFC_B200_ENOMEM, "grid too small to stage the patch table");
+    PatchDesc *pd = reinterpret_cast<PatchDesc *>(scr + used);
+    used = 0;
+    for (int d = 0; d < S.nd; d++) {
+        const size_t n = (size_t)g.N[d] + 1;
+        CK(cudaMemcpyAsync(scr + used, cc[d], n*sizeof(double), cudaMemcpyHostToDevice, S.st));
+        a.cc[d] = scr + used;
+        used += (n + 15)/16*16;
+    }
+    CK(cudaMemcpyAsync(pd, patches, (size_t)num_patches*sizeof(PatchDesc), cudaMemcpyHostToDevice, S.st));
+    a.patches = pd;
+    CK(cudaMemsetAsync(S.state[S.cur], 0, field_bytes()*S.E, S.st));   // ghosts: rebuilt by every RHS evaluation
+    {
+        Scope sc(KC_PATCH);
+        const int n = launch_patches(S.nf, S.nd, a, S.st);
+        if (!n) return fail(MFC_B200_EUNSUPPORTED, "no patch kernel instantiated for this (num_fluids, num_dims)");
+        sc.done(n);
+    }
+    CK(cudaStreamSynchronize(S.st));
+    CK(cudaGetLastError());
     S.uploaded = true;
     return 0;
 }

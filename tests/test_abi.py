@@ -67,6 +67,29 @@ int main(void) {
     assert got == want
 
 
+def test_patch_struct_layout_matches_the_header():
+    """mfc_b200_patch_t (device-side initial condition): header == ctypes mirror."""
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mfc_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mfc_b200_patch_t), offsetof(mfc_b200_patch_t, alter_patch),
+         offsetof(mfc_b200_patch_t, x_centroid), offsetof(mfc_b200_patch_t, radii), offsetof(mfc_b200_patch_t, smooth_coeff),
+         offsetof(mfc_b200_patch_t, pres), offsetof(mfc_b200_patch_t, alpha));
+  return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "t.c"), os.path.join(td, "t")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        got = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
+    P = abi.Patch
+    want = [C.sizeof(P), P.alter_patch.offset, P.x_centroid.offset, P.radii.offset, P.smooth_coeff.offset, P.pres.offset,
+            P.alpha.offset]
+    assert got == want and abi.MAX_PATCHES == 10
+
+
 def _params(cfg, cb):
     lay = rank_layout(0, 1, cfg)
     met = ghosted_metrics(lay, cfg, cb, [lay])

@@ -39,3 +39,20 @@ def test_params_type_member_order_matches_ctypes_mirror():
                 members.append(re.sub(r"\(.*", "", m))
     members = [m for m in members if m and m != ")"]
     assert members == [f[0] for f in abi.Params._fields_], members
+
+
+def _members(type_name):
+    body = re.search(r"type, bind\(C\) :: %s(.*?)end type" % type_name, SRC, re.S).group(1)
+    members = []
+    for line in body.splitlines():
+        line = line.split("!")[0]
+        if "::" not in line:
+            continue
+        for m in re.sub(r"\([^)]*\)", "", line.split("::")[1]).split(","):
+            if m.strip():
+                members.append(m.strip())
+    return members
+
+
+def test_patch_type_member_order_matches_ctypes_mirror():
+    assert _members("mfc_b200_patch_t") == [f[0] for f in abi.Patch._fields_]
