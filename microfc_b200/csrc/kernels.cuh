@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
     constexpr int NS = march_slots(DIR, ND);           // slots per warp: ring | rin | qin (RK) | outs
-    constexpr int NB = R + 2;                          // mbarriers per warp: ring slots, rin, qin
+    constexpr int NB = R + 1;                          // mbarriers per warp: ring slots, operand rows (rin + qin)
     constexpr unsigned kRowBytes = (unsigned)(E*kWY*sizeof(double));
     static_assert(R >= 6, "the ring holds the 5 live rows of the stencil plus at least one row in flight");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -957,7 +957,7 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
     double *ring = reinterpret_cast<double *>(smem_raw) + warp*(NS*SLOT);
     double *rin = ring + R*SLOT, *qin = rin + SLOT, *outs = ring + (NS - 1)*SLOT;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsY*NS*SLOT) + warp*NB;
-    unsigned long long *bar_r = bar + R, *bar_q = bar + R + 1;
+    unsigned long long *bar_r = bar + R;
     const int j0 = (blockIdx.x*kWarpsY + warp)*kWY;
     if (j0 > g.N[0]) return;                           // whole warp out of range (no block barriers below)
     const bool on = j0 + lane <= g.N[0];
@@ -981,13 +981,10 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
             mbar_expect_tx(&bar[r - r_first], kRowBytes);
             tma_load_row(ring + (r - r_first)*SLOT, &a.tm_q, cx, DIR == 1 ? cy + r : cy, DIR == 1 ? cz : cz + r, &bar[r - r_first]);
         }
-        // operands of the first cell finished (s0)
-        mbar_expect_tx(bar_r, kRowBytes);
+        // operands of the first cell finished (s0): both rows complete the same barrier
+        mbar_expect_tx(bar_r, need_q1 ? 2*kRowBytes : kRowBytes);
         tma_load_row(rin, &a.tm_rhs_i, j0, DIR == 1 ? s0 : t, DIR == 1 ? t : s0, bar_r);
-        if (need_q1) {
-            mbar_expect_tx(bar_q, kRowBytes);
-            tma_load_row(qin, &a.tm_q1_i, j0, DIR == 1 ? s0 : t, DIR == 1 ? t : s0, bar_q);
-        }
+        if (need_q1) tma_load_row(qin, &a.tm_q1_i, j0, DIR == 1 ? s0 : t, DIR == 1 ? t : s0, bar_r);
     }
     int next_issue = r_first + R;                      // only lane 0 issues, every lane counts
 
@@ -1038,7 +1035,6 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
                 for (int v = 0; v < E; v++) in.r[v] = rin[v*kWY + lane];
                 if (RK) {
                     if (need_q1) {
-                        mbar_wait(bar_q, phase_op);
 #pragma unroll
                         for (int v = 0; v < E; v++) in.q1[v] = qin[v*kWY + lane];
                     }
@@ -1089,12 +1085,9 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
             if (fin) {
                 tma_store_row(&a.tm_out_i, j0, DIR == 1 ? s - 1 : t, DIR == 1 ? t : s - 1, outs);
                 if (s <= s1) {                         // operands of cell s, finished by the next iteration
-                    mbar_expect_tx(bar_r, kRowBytes);
+                    mbar_expect_tx(bar_r, need_q1 ? 2*kRowBytes : kRowBytes);
                     tma_load_row(rin, &a.tm_rhs_i, j0, DIR == 1 ? s : t, DIR == 1 ? t : s, bar_r);
-                    if (need_q1) {
-                        mbar_expect_tx(bar_q, kRowBytes);
-                        tma_load_row(qin, &a.tm_q1_i, j0, DIR == 1 ? s : t, DIR == 1 ? t : s, bar_q);
-                    }
+                    if (need_q1) tma_load_row(qin, &a.tm_q1_i, j0, DIR == 1 ? s : t, DIR == 1 ? t : s, bar_r);
                 }
             }
             if (next_issue <= r_last) {
@@ -1160,6 +1153,14 @@ __device__ __forceinline__ void bc_decode(const GridDesc &g, int dir, long long 
     if (dir == 0) { n0 = g.N[1] + 1; o0 = 0; n1 = g.N[2] + 1; o1 = 0; }
     else if (dir == 1) { n0 = g.N[0] + 1 + 2*g.b; o0 = -g.b; n1 = g.N[2] + 1; o1 = 0; }
     else { n0 = g.N[0] + 1 + 2*g.b; o0 = -g.b; n1 = g.N[1] + 1 + 2*g.b; o1 = -g.b; }
+    if (dir == 0) {
+        // x slabs: the layer runs fastest, so that the b ghost cells of one row (contiguous in
+        // memory, one 32-byte sector for b = 4) are written by neighbouring threads
+        layer = (int)(idx % g.b); idx /= g.b;
+        t0 = (int)(idx % n0) + o0; idx /= n0;
+        t1 = (int)idx + o1;
+        return;
+    }
     t0 = (int)(idx % n0) + o0; idx /= n0;
     t1 = (int)(idx % n1) + o1; idx /= n1;
     layer = (int)idx;                              // 0 .. b-1
