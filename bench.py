@@ -35,6 +35,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout
+# when NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 from microfc_b200 import cases, pre_process  # noqa: E402
 from microfc_b200.case import CaseConfig  # noqa: E402
