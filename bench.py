@@ -8,7 +8,8 @@ One "step" is one SSP-RK3 time step (3 RHS evaluations: ghost fill, cons->prim, 
 HLLC sweeps with the update fused into the last sweep, plus the ICFL diagnostic) on the
 workload BASELINE.json's target names: the synthetic 3-D two-fluid shock-bubble at 512^3 cells
 PER GPU (configs[4]), weak-scaled over N GPUs with the reference's block decomposition and an
-NCCL halo exchange.  Other BASELINE configs: --workload advection_2d_1024 | shockbubble_2d_4096.
+NCCL halo exchange.  Other BASELINE configs: --workload advection_2d_1024 | shockbubble_2d_4096 |
+shockdroplet_2d_viscous_2048.
 
 Printed JSON (rank 0, one line):
   value      Mcell-steps/s of the whole job, state resident in HBM, timed with CUDA events on
@@ -53,6 +54,8 @@ HLLC_FLOPS = {1: 170, 2: 206, 3: 250}   # per face, m_riemann_solvers.fpp:136-32
 DIV_FLOPS = 35             # flux divergence + source per direction, m_rhs.fpp:565-653
 PRIM_FLOPS = 22
 TOPOLOGY = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# 2-D workloads: the reference's rule gives 4 x 2 on 8 ranks (ties -> larger px, m_mpi_proxy.fpp:177-203)
+TOPOLOGY_2D = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (4, 2, 1)}
 
 
 def sweep_flops_per_cell(E: int, nd: int, with_rk: bool) -> int:
@@ -65,7 +68,7 @@ def step_flops_per_cell(E: int, nd: int) -> int:
 
 
 def workload_case(name: str, n_gpus: int, cells: int | None):
-    px, py, pz = TOPOLOGY[n_gpus]
+    px, py, pz = TOPOLOGY[n_gpus] if name == "shockbubble_3d_512" else TOPOLOGY_2D[n_gpus]
     if name == "shockbubble_3d_512":
         nc = cells or 512
         d = cases.shockbubble_3d(ncx=nc * px, ncy=nc * py, ncz=nc * pz, Nt=10 ** 6)
@@ -79,9 +82,14 @@ def workload_case(name: str, n_gpus: int, cells: int | None):
         d = cases.advection_2d(N=nc * px - 1, Nt=10 ** 6)
         d['n'] = nc * py - 1
         desc = f"examples/2D_advection at {nc}^2 cells per GPU (BASELINE configs[1])"
+    elif name == "shockdroplet_2d_viscous_2048":
+        nc = cells or 2048
+        d = cases.shockdroplet_2d(Nx=nc * px - 1, Ny=nc * py - 1, Nt=10 ** 6, viscous=True)
+        desc = (f"examples/2D_shockdroplet with viscous fluxes (fluid_pp%Re as in examples/2D_viscous), {nc}^2 cells per GPU "
+                "(BASELINE configs[3]: 8192x4096 on 8 GPUs)")
     else:
         raise SystemExit(f"unknown workload {name}")
-    return cases.config(d), desc
+    return cases.config(d), desc, (px, py, pz)
 
 
 class ClockSampler:
@@ -140,8 +148,12 @@ def cpu_reference_run(cfg_full: CaseConfig, steps: int, warmup: int, sample_cell
         d = cases.shockbubble_3d(nc=sample_cells, Nt=10 ** 6)
         sample = f"{sample_cells}^3 cells of the same 3-D shock-bubble case"
     else:
-        d = cases.shockbubble_2d_cells(sample_cells, sample_cells, Nt=10 ** 6) if cfg_full.bc[0][0] == -6 \
-            else cases.advection_2d(N=sample_cells - 1, Nt=10 ** 6)
+        if cfg_full.viscous:
+            d = cases.shockdroplet_2d(Nx=sample_cells - 1, Ny=sample_cells - 1, Nt=10 ** 6, viscous=True)
+        elif cfg_full.bc[0][0] == -6:
+            d = cases.shockbubble_2d_cells(sample_cells, sample_cells, Nt=10 ** 6)
+        else:
+            d = cases.advection_2d(N=sample_cells - 1, Nt=10 ** 6)
         sample = f"{sample_cells}^2 cells of the same 2-D case"
     cfg = cases.config(d)
     cb = pre_process.generate_grid(cfg)
@@ -179,12 +191,12 @@ def main():
     if args.gpus not in TOPOLOGY:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
     K, W = args.steps, max(args.warmup, 0)
-    cfg, desc = workload_case(args.workload, args.gpus, args.cells)
+    cfg, desc, topo = workload_case(args.workload, args.gpus, args.cells)
     nd, E = cfg.num_dims, cfg.sys_size
     ncell_total = int(np.prod(cfg.shape_glb))
     config = {"workload": desc, "cells_total": ncell_total, "cells_per_gpu": ncell_total // args.gpus,
               "sys_size": E, "num_dims": nd, "time_stepper": "SSP-RK3", "weno_order": 5, "riemann_solver": "HLLC",
-              "run_time_info": bool(cfg.run_time_info), "decomposition": "x".join(map(str, TOPOLOGY[args.gpus])),
+              "run_time_info": bool(cfg.run_time_info), "decomposition": "x".join(map(str, topo)),
               "l2": "state (>= 9 GB per GPU at the default size) is far larger than the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -261,8 +273,11 @@ def main():
     prof = sim.profile_report()
     sim.profile(False)
     clocks = sampler.stop()
-    if not (icfl == icfl) or (cfg.run_time_info and icfl > 1.0):
-        raise SystemExit(f"unstable run: ICFL = {icfl}")
+    if cfg.run_time_info:
+        if not (icfl == icfl) or icfl > 1.0:
+            raise SystemExit(f"unstable run: ICFL = {icfl}")
+    elif not np.isfinite(sim.download()).all():      # run_time_info = F (2D_shockdroplet): no ICFL row to watch
+        raise SystemExit("unstable run: non-finite state")
     value = ncell_total * K / secs / 1e6
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
