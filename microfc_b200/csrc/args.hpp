@@ -53,6 +53,7 @@ struct SweepArgs {
     // of every face it solves, for k_visc (m_riemann_solvers.fpp:225-230,314-324)
     double *visc_face;
     double Res[2][kMaxFluids];
+    double iRes[2][kMaxFluids];  // 1/Res (fast build: the face stores 1/Re_avg, no divisions)
     int Re_idx[2][kMaxFluids], Re_size[2];
 };
 
@@ -72,6 +73,15 @@ struct ViscArgs {
     int dir, nf, weno_Re_flux;
     int bc_beg, bc_end;
     int Re_size[2];
+    // fast build: reciprocals of the centre-to-centre distances, rdcc(i) = 1/(s_cc(i+1) - s_cc(i)) for
+    // i = -b .. N+b-1, and of the cell widths
+    const double *rdcc[3], *rds[3];
+    // last direction: the TVD-RK statement rk_mode (1..4, 0 = store the RHS) is applied here
+    // instead of by a separate k_rk pass; E variables, q1 = q_cons_ts(1), qs = stage state
+    int rk_mode, E;
+    const double *q1, *qs;
+    double *qout;
+    double dt;
 };
 
 // the TVD-RK statement as a separate pass (viscous runs, where it cannot be fused into the sweep)

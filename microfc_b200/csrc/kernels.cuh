@@ -353,11 +353,30 @@ __device__ __forceinline__ void face_reynolds(const double *L, const double *R, 
         Re_avg[i] = 2.0/(1.0/Re_L + 1.0/Re_R);
     }
 }
-// vel_src (ND planes) and Re_avg (2 planes) of the face whose LEFT cell has in-plane offset off
+// vel_src (ND planes) and Re_avg (2 planes) of the face whose LEFT cell has in-plane offset off.
+// Fast build: 1/Re_avg = (max(sum alpha_L/Res, eps) + max(sum alpha_R/Res, eps))/2 is stored instead
+// (the same quantity, :225-230, without its five divisions); k_visc multiplies by it.
 template <int NF, int ND>
 __device__ __forceinline__ void store_visc_face(const SweepArgs &a, unsigned off, const double *L, const double *R, const double *vs) {
+    constexpr int ADV = NF + ND + 1;
     double Re_avg[2];
+#if MFC_STRICT
     face_reynolds<NF, ND>(L, R, a, Re_avg);
+#else
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double rl = a.Re_size[i] > 0 ? 0.0 : -1e6, rr = rl;
+        for (int q = 0; q < a.Re_size[i]; q++) {
+            double al = L[ADV], ar = R[ADV];
+#pragma unroll
+            for (int f = 1; f < NF; f++)
+                if (a.Re_idx[i][q] == f) { al = L[ADV + f]; ar = R[ADV + f]; }
+            rl = fma(al, a.iRes[i][q], rl);
+            rr = fma(ar, a.iRes[i][q], rr);
+        }
+        Re_avg[i] = 0.5*(fmax(rl, 1e-16) + fmax(rr, 1e-16));
+    }
+#endif
     const long long fs = a.g.fstride;
 #pragma unroll
     for (int i = 0; i < ND; i++) a.visc_face[i*fs + off] = vs[i];
@@ -1326,15 +1345,24 @@ __global__ void __launch_bounds__(128) k_visc_grad(const __grid_constant__ ViscA
         }
 }
 
-template <int ND>
-__global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a) {
+// x / Re_avg: the strict build divides (m_riemann_solvers.fpp:722-899 as written); the fast build
+// multiplies by the 1/Re_avg the sweep stored
+#if MFC_STRICT
+#define VDIV(x, re) ((x)/(re))
+#define VDIV3(x, re) ((x)/(3.0*(re)))
+#else
+#define VDIV(x, re) ((x)*(re))
+#define VDIV3(x, re) ((x)*((1.0/3.0)*(re)))
+#endif
+template <int NF, int ND>
+__global__ void __launch_bounds__(128, 4) k_visc(const __grid_constant__ ViscArgs a) {
     const GridDesc &g = a.g;
     const int j = blockIdx.x*blockDim.x + threadIdx.x, k = blockIdx.y;
     if (j > g.N[0]) return;
     const int id = a.dir, b = g.b;
     const int c[3] = {j, k, 0};
     const long long cell = g.at(j, k, 0), fs = g.fstride, sid = g.stride(id);
-    const int MOM = a.nf, EN = a.nf + ND;
+    constexpr int E = 2*NF + ND + 1, MOM = NF, EN = NF + ND;
     double fm[2][ND], fe[2];                       // flux_src(mom), flux_src(E) of faces c-1/2 and c+1/2
 #pragma unroll
     for (int side = 0; side < 2; side++) {
@@ -1364,14 +1392,24 @@ __global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a
                     const double *u = a.prim + v*fs;
                     if (dd == id) {
                         const double *cc = a.cc[id] + b;
+#if MFC_STRICT
                         dR = (u[cr] - u[cl])/(cc[f + 1] - cc[f]);    // dqR(c) :237-248 == dqL(c+1) :224-235
+#else
+                        dR = (u[cr] - u[cl])*a.rdcc[id][f + b];
+#endif
                         dL = dR;
                     } else {
                         const long long sd = g.stride(dd);
                         const double *cc = a.cc[dd] + b;
                         const int t = c[dd];
+#if MFC_STRICT
                         const double sLr = (u[cr] - u[cr - sd])/(cc[t] - cc[t - 1]), sRr = (u[cr + sd] - u[cr])/(cc[t + 1] - cc[t]);
                         const double sLl = (u[cl] - u[cl - sd])/(cc[t] - cc[t - 1]), sRl = (u[cl + sd] - u[cl])/(cc[t + 1] - cc[t]);
+#else
+                        const double rm = a.rdcc[dd][t - 1 + b], rp = a.rdcc[dd][t + b];
+                        const double sLr = (u[cr] - u[cr - sd])*rm, sRr = (u[cr + sd] - u[cr])*rp;
+                        const double sLl = (u[cl] - u[cl - sd])*rm, sRl = (u[cl + sd] - u[cl])*rp;
+#endif
                         dR = 25e-2*(sLr + sRr + sLl + sRl);          // :300-307 at the left cell == :283-290 at the right cell
                         dL = dR;
                     }
@@ -1383,18 +1421,18 @@ __global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a
         for (int i = 0; i < ND; i++) m[i] = 0.0;
         if (id == 0) {
             if (a.Re_size[0] > 0) {                // :714-736
-                const double tau = (4.0/3.0)*avg[0][0]/Re_avg[0];
+                const double tau = VDIV((4.0/3.0)*avg[0][0], Re_avg[0]);
                 m[0] = m[0] - tau; e = e - vsrc[0]*tau;
             }
             if (a.Re_size[1] > 0) {                // :738-760
-                const double tau = avg[0][0]/Re_avg[1];
+                const double tau = VDIV(avg[0][0], Re_avg[1]);
                 m[0] = m[0] - tau; e = e - vsrc[0]*tau;
             }
             if (ND > 1) {
                 if (a.Re_size[0] > 0) {            // :764-801
                     double tau[2];
-                    tau[0] = -(2.0/3.0)*avg[ND > 1 ? 1 : 0][ND > 1 ? 1 : 0]/Re_avg[0];
-                    tau[1] = (avg[ND > 1 ? 1 : 0][0] + avg[0][ND > 1 ? 1 : 0])/Re_avg[0];
+                    tau[0] = VDIV(-(2.0/3.0)*avg[ND > 1 ? 1 : 0][ND > 1 ? 1 : 0], Re_avg[0]);
+                    tau[1] = VDIV(avg[ND > 1 ? 1 : 0][0] + avg[0][ND > 1 ? 1 : 0], Re_avg[0]);
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
                         m[ND > 1 ? i : 0] = m[ND > 1 ? i : 0] - tau[i];
@@ -1402,7 +1440,7 @@ __global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a
                     }
                 }
                 if (a.Re_size[1] > 0) {            // :803-825
-                    const double tau = avg[ND > 1 ? 1 : 0][ND > 1 ? 1 : 0]/Re_avg[1];
+                    const double tau = VDIV(avg[ND > 1 ? 1 : 0][ND > 1 ? 1 : 0], Re_avg[1]);
                     m[0] = m[0] - tau; e = e - vsrc[0]*tau;
                 }
             }
@@ -1410,8 +1448,8 @@ __global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a
             constexpr int Y = ND > 1 ? 1 : 0;
             if (a.Re_size[0] > 0) {                // :831-872
                 double tau[2];
-                tau[0] = (avg[Y][0] + avg[0][Y])/Re_avg[0];
-                tau[1] = (4.0*avg[Y][Y] - 2.0*avg[0][0])/(3.0*Re_avg[0]);
+                tau[0] = VDIV(avg[Y][0] + avg[0][Y], Re_avg[0]);
+                tau[1] = VDIV3(4.0*avg[Y][Y] - 2.0*avg[0][0], Re_avg[0]);
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     m[ND > 1 ? i : 0] = m[ND > 1 ? i : 0] - tau[i];
@@ -1419,7 +1457,7 @@ __global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a
                 }
             }
             if (a.Re_size[1] > 0) {                // :874-899
-                const double tau = (avg[0][0] + avg[Y][Y])/Re_avg[1];
+                const double tau = VDIV(avg[0][0] + avg[Y][Y], Re_avg[1]);
                 m[Y] = m[Y] - tau; e = e - vsrc[Y]*tau;
             }
         }
@@ -1427,15 +1465,41 @@ __global__ void __launch_bounds__(128) k_visc(const __grid_constant__ ViscArgs a
         for (int i = 0; i < ND; i++) fm[side][i] = m[i];
         fe[side] = e;
     }
-    const double dsj = a.ds[id][c[id] + b];        // m_rhs.fpp:591-604, :639-652
+    // m_rhs.fpp:591-604, :639-652
+#if MFC_STRICT
+    const double dsj = a.ds[id][c[id] + b];
+#define MFC_VADD(r, d) ((r) + 1.0/dsj*(d))
+#else
+    const double rdsj = a.rds[id][c[id] + b];
+#define MFC_VADD(r, d) fma(rdsj, (d), (r))
+#endif
+    if (a.rk_mode == 0) {
 #pragma unroll
-    for (int i = 0; i < ND; i++) {
-        double *r = a.rhs + (MOM + i)*fs + cell;
-        *r = *r + 1.0/dsj*(fm[0][i] - fm[1][i]);
+        for (int i = 0; i < ND; i++) {
+            double *r = a.rhs + (MOM + i)*fs + cell;
+            *r = MFC_VADD(*r, fm[0][i] - fm[1][i]);
+        }
+        double *r = a.rhs + EN*fs + cell;
+        *r = MFC_VADD(*r, fe[0] - fe[1]);
+        return;
     }
-    double *r = a.rhs + EN*fs + cell;
-    *r = *r + 1.0/dsj*(fe[0] - fe[1]);
+    // last direction: the RHS is complete here -- apply the TVD-RK statement
+    // (m_time_steppers.fpp:167,245,322,342) instead of storing it for a separate pass
+    double r[E], q1[E], qs[E];
+#pragma unroll
+    for (int v = 0; v < E; v++) {                  // all loads first: 3 E independent requests in flight
+        const long long o = v*fs + cell;
+        r[v] = a.rhs[o]; q1[v] = a.q1[o]; qs[v] = a.qs[o];
+    }
+#pragma unroll
+    for (int i = 0; i < ND; i++) r[MOM + i] = MFC_VADD(r[MOM + i], fm[0][i] - fm[1][i]);
+    r[EN] = MFC_VADD(r[EN], fe[0] - fe[1]);
+#pragma unroll
+    for (int v = 0; v < E; v++) a.qout[v*fs + cell] = rk_apply(a.rk_mode, q1[v], qs[v], r[v], a.dt);
+#undef MFC_VADD
 }
+#undef VDIV
+#undef VDIV3
 
 // the TVD-RK statement on its own (m_time_steppers.fpp:167,245,322,342), interior cells only
 __global__ void __launch_bounds__(256) k_rk(const __grid_constant__ RkArgs a) {

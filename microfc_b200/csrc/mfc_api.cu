@@ -86,6 +86,7 @@ struct Sim {
     double cuni[3][kNumWenoCoef];
     int variant = 2;                   // sweep kernel generation (MFC_B200_KERNELS=1 selects the v1 kernels)
     double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr}, *cc[3] = {nullptr, nullptr, nullptr};
+    double *rdcc[3] = {nullptr, nullptr, nullptr};   // 1/(s_cc(i+1) - s_cc(i)), viscous fast build
     // viscous runs: vel_src + Re_avg per face (nd+2 planes), dq_prim_d (nd*nd planes, weno_Re_flux)
     double *visc_face = nullptr, *visc_grad = nullptr;
     double Res[2][kMaxFluids];
@@ -153,7 +154,7 @@ void free_all() {
     for (auto &s : S.state) fr(s);
     fr(S.prim); fr(S.rhs); fr(S.snap); fr(S.visc_face); fr(S.visc_grad);
     for (int d = 0; d < 3; d++) {
-        fr(S.coef[d]); fr(S.rds[d]); fr(S.ds[d]); fr(S.cc[d]);
+        fr(S.coef[d]); fr(S.rds[d]); fr(S.ds[d]); fr(S.cc[d]); fr(S.rdcc[d]);
         for (int s = 0; s < 2; s++) { fr(S.sendbuf[d][s]); fr(S.recvbuf[d][s]); }
     }
     if (S.stab_dev) { cudaFree(S.stab_dev); S.stab_dev = nullptr; }
@@ -380,7 +381,11 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     ViscArgs va{};
     if (S.viscous) {                                         // :456-464 s_get_viscous
         va.g = S.g; va.prim = S.prim; va.visc_face = S.visc_face; va.grad = S.visc_grad; va.rhs = S.rhs;
-        for (int d = 0; d < 3; d++) { va.coef[d] = S.coef[d]; va.clen[d] = S.clen[d]; va.coef_lo[d] = S.coef_lo[d]; va.cc[d] = S.cc[d]; va.ds[d] = S.ds[d]; }
+        for (int d = 0; d < 3; d++) {
+            va.coef[d] = S.coef[d]; va.clen[d] = S.clen[d]; va.coef_lo[d] = S.coef_lo[d]; va.cc[d] = S.cc[d]; va.ds[d] = S.ds[d];
+            va.rdcc[d] = S.rdcc[d]; va.rds[d] = S.rds[d];
+        }
+        va.rk_mode = 0; va.E = S.E; va.q1 = q1; va.qs = q; va.qout = qout; va.dt = dt;
         va.eps = S.p.weno_eps; va.nf = S.nf; va.weno_Re_flux = S.p.weno_Re_flux;
         va.Re_size[0] = S.Re_size[0]; va.Re_size[1] = S.Re_size[1];
         if (S.p.weno_Re_flux) { Scope sc(KC_VISC); sc.done(S.L->visc_grad(S.nd, va, S.st)); }
@@ -397,7 +402,10 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.visc_face = S.viscous ? S.visc_face : nullptr;
         for (int i = 0; i < 2; i++) {
             a.Re_size[i] = S.Re_size[i];
-            for (int k = 0; k < kMaxFluids; k++) { a.Res[i][k] = S.Res[i][k]; a.Re_idx[i][k] = S.Re_idx[i][k]; }
+            for (int k = 0; k < kMaxFluids; k++) {
+                a.Res[i][k] = S.Res[i][k]; a.Re_idx[i][k] = S.Re_idx[i][k];
+                a.iRes[i][k] = k < S.Re_size[i] ? 1.0/S.Res[i][k] : 0.0;
+            }
         }
         a.variant = S.variant; a.coef_uniform = S.coef_uniform[d]; a.weno_order = S.p.weno_order;
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
@@ -420,12 +428,11 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         if (fuse_stab && d == 0 && (rc = stab_reduce_and_copy())) return rc;
         if (S.viscous) {                                     // m_rhs.fpp:591-604, :639-652
             va.dir = d; va.bc_beg = S.p.bc[2*d]; va.bc_end = S.p.bc[2*d + 1];
+            // the RK statement cannot be fused into the last sweep (the viscous terms come after
+            // it); it is applied by the last direction's k_visc, which completes the RHS
+            va.rk_mode = d == S.nd - 1 ? rk_mode : 0;
             Scope sv(KC_VISC); sv.done(S.L->visc(S.nd, va, S.st));
         }
-    }
-    if (S.viscous && rk_mode != 0) {                         // the RK statement cannot be fused into the last sweep
-        RkArgs r{S.g, q1, q, S.rhs, qout, dt, rk_mode, S.E};
-        Scope sr(KC_RK); sr.done(S.L->rk(r, S.st));
     }
     return 0;
 }
@@ -592,11 +599,18 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
                 -1.0/6, 2.0/3, 1.0/3, 1.0/6, 5.0/6, -1.0/3,              // poly_coef_cbR
                 0.1, 0.6, 0.3, 0.3, 0.6, 0.1,                            // d_cbL, d_cbR
                 4.0/3, -11.0/3, 10.0/3, 4.0/3, -5.0/3, 4.0/3, 10.0/3, -11.0/3, 4.0/3};   // beta_coef
+            // Tolerance: the tables are computed from the cell-boundary coordinates, whose own
+            // rounding (eps |s| against a width ds) reappears in the coefficients amplified by
+            // |s|/ds; a deviation explainable by that noise is the uniform grid the user asked for.
+            double smax = 0.0, dsmin = 1e300;
+            for (int i = 0; i < N + 2 + 2*b; i++) smax = std::fmax(smax, std::fabs(p->cb[d][i]));
+            for (int i = 0; i < N + 1 + 2*b; i++) dsmin = std::fmin(dsmin, p->ds[d][i]);
+            const double tol = std::fmax(1e-12, 16.0*2.220446049250313e-16*smax/dsmin);
             bool uni = true;
             for (int c = 0; c < kNumWenoCoef; c++) {
                 S.cuni[d][c] = classic[c];
                 for (int i = 0; i < t.len && uni; i++)
-                    if (std::fabs(t.data[(size_t)c*t.len + i] - classic[c]) > 1e-12) uni = false;
+                    if (std::fabs(t.data[(size_t)c*t.len + i] - classic[c]) > tol) uni = false;
             }
             S.coef_uniform[d] = (uni && p->weno_order == 5) ? 1 : 0;
         }
@@ -610,6 +624,10 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         CK(cudaMemcpy(S.ds[d], p->ds[d], r.size()*sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&S.cc[d], r.size()*sizeof(double)));
         CK(cudaMemcpy(S.cc[d], p->cc[d], r.size()*sizeof(double), cudaMemcpyHostToDevice));
+        for (size_t i = 0; i + 1 < r.size(); i++) r[i] = 1.0/(p->cc[d][i + 1] - p->cc[d][i]);
+        r[r.size() - 1] = 0.0;
+        CK(cudaMalloc(&S.rdcc[d], r.size()*sizeof(double)));
+        CK(cudaMemcpy(S.rdcc[d], r.data(), r.size()*sizeof(double), cudaMemcpyHostToDevice));
         for (int s = 0; s < 2; s++)
             if (S.bc[d][s] >= 0) {
                 const size_t n = (size_t)slab_count(S.g, d)*S.E*sizeof(double);
