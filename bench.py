@@ -36,9 +36,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout
-# when NCCL_DEBUG is set) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its "NCCL version
+# ..." banner to stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for
+# the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 from microfc_b200 import cases, pre_process  # noqa: E402
 from microfc_b200.case import CaseConfig  # noqa: E402
@@ -214,7 +220,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -351,7 +357,7 @@ def main():
                 "e2e": e2e, "gpu_launches": launches * world, "clocks": clocks,
                 "roofline": roof, "roofline_hbm": roof_hbm, "kernel_time": kernel_share, "cpu_baseline": cpu,
                 "icfl_last": icfl}
-        print(json.dumps(line))
+        emit(line)
     sim.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -28,6 +28,10 @@ struct SweepArgs {
     int rk_mode;           // 0: store RHS; 1..4: fused update, see rk_apply()
     int seg;               // cells per thread along the sweep (march kernels)
     int rows;              // rows per block (x kernel)
+    // x kernel, split launch: CTA blockIdx.x works on x tile blockIdx.x (< xb_n0) or blockIdx.x +
+    // xb_skip; xsplit = 1: interior tiles only (no x ghost column read), 2: the remaining tiles,
+    // 0: everything in one launch
+    int xsplit, xb_n0, xb_skip;
     // fused stability criterion (x kernel of stage 1, inviscid fast build): ICFL max of the
     // cells this kernel finishes, m_data_output.fpp:215-233; nullptr = off
     unsigned long long *stab_out;

@@ -838,7 +838,10 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsX*R*SLOT) + warp*R;
-    const int jw = (blockIdx.x*kWarpsX + warp)*kWarpCells;   // first cell finished by this warp
+    // x tile of this CTA.  A multi-rank run launches the x sweep in two parts (xsplit): the tiles
+    // that read no x ghost column first, while the x halo is still in flight, then the rest.
+    const int bx = (int)blockIdx.x < a.xb_n0 ? (int)blockIdx.x : (int)blockIdx.x + a.xb_skip;
+    const int jw = (bx*kWarpsX + warp)*kWarpCells;           // first cell finished by this warp
     if (jw > g.N[0]) return;                           // whole warp out of range (no block barriers below)
     const int k0 = blockIdx.y*a.rows, l = blockIdx.z;
     const int nrows = min(a.rows, g.N[1] + 1 - k0);

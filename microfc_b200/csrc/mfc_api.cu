@@ -411,7 +411,9 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
-        if ((rc = ghosts_ready(q, d))) return rc;
+        // multi-rank, x halo still in flight: sweep the tiles that read no x ghost column first
+        const bool split_x = d == 0 && S.overlap && S.halo_pending[0] && S.nd >= 2;
+        if (!split_x && (rc = ghosts_ready(q, d))) return rc;
         {
             const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
             if (!tq || !t1) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
@@ -422,8 +424,19 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
             a.tm_rhs_i = S.tm_rhs[2]; a.tm_q1_i = *t1i; a.tm_out_i = *toi;
         }
         Scope sc(KC_SWEEP_X + d);
-        const int n = S.L->sweep(S.nf, S.nd, d, a, S.st);
-        if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
+        int n = 0;
+        if (split_x) {
+            a.xsplit = 1;
+            const int n1 = S.L->sweep(S.nf, S.nd, d, a, S.st);
+            if (!n1) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
+            if ((rc = ghosts_ready(q, d))) return rc;
+            a.xsplit = 2;
+            const int n2 = S.L->sweep(S.nf, S.nd, d, a, S.st);
+            n = (n1 > 0 ? n1 : 0) + (n2 > 0 ? n2 : 0);
+        } else {
+            n = S.L->sweep(S.nf, S.nd, d, a, S.st);
+            if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
+        }
         sc.done(n);
         if (fuse_stab && d == 0 && (rc = stab_reduce_and_copy())) return rc;
         if (S.viscous) {                                     // m_rhs.fpp:591-604, :639-652
@@ -656,7 +669,11 @@ int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
     ncclUniqueId u;
     std::memcpy(&u, id, 128);
     NK(S.nccl.CommInitRank(&S.comm, nranks, u, rank));
-    CK(cudaStreamCreateWithFlags(&S.cs, cudaStreamNonBlocking));
+    {   // halo traffic ahead of the sweeps' CTAs whenever an SM slot frees up
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&S.cs, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&S.ev_q, cudaEventDisableTiming));
     for (auto &e : S.ev_halo) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     {
