@@ -308,14 +308,14 @@ def main():
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     hbm_peak, hbm_src, fp64_peak, fp64_src = measured_peaks()
-    sweeps = {k: v for k, v in prof.items() if k.startswith("k_sweep") and v[1] > 0}
+    sweeps = {k: v for k, v in prof.items() if k in ("k_xrow", "k_march3<y>", "k_march3<z>") and v[1] > 0}
     dom = max(sweeps, key=lambda k: sweeps[k][0])
     dom_t = sweeps[dom][0] / sweeps[dom][1]                      # average launch duration (CUDA events)
-    last_dir = {1: "k_sweep_x", 2: "k_sweep_march<y>", 3: "k_sweep_march<z>"}[nd]
+    last_dir = {1: "k_xrow", 2: "k_march3<y>", 3: "k_march3<z>"}[nd]
     cells_gpu = ncell_total // args.gpus
     dom_flops = sweep_flops_per_cell(E, nd, dom == last_dir) * cells_gpu
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_v3a_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r01_v4_traffic.json")
     if os.path.exists(tp) and nd == 3 and E == 8:
         # DRAM bytes per cell of this kernel from the committed ncu --set full capture (256^3, same
         # kernels): one stage-1 launch and two stage-2/3 launches per step

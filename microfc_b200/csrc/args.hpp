@@ -14,7 +14,7 @@ struct alignas(64) TensorMap {
 struct SweepArgs {
     GridDesc g;
     const double *q;       // stage state, conservative (alpha_rho, mom, E, alpha), ghosts filled
-    const double *prim;    // velocity (nd fields) + pressure of the stage state, ghosted
+    const double *prim;    // velocity (nd fields) + pressure of the stage state (viscous runs: k_prim)
     double *rhs;           // accumulated RHS (same padded layout)
     const double *q1;      // q_cons_ts(1) for the fused RK update
     double *qout;          // updated state
@@ -37,7 +37,6 @@ struct SweepArgs {
     unsigned long long *stab_out;
     const double *rds_t[2];      // 1/ds of the two transverse directions (y, z)
     int weno_order;        // 5, 3 or 1
-    int variant;           // 2: TMA-ring kernels (k_xrow / k_march2), 1: v1 direct-load kernels
     int coef_uniform;      // 1: cuni[] holds the coefficients of every cell of this direction
     double cuni[kNumWenoCoef];   // uniform-grid WENO coefficients (COEF = 0 kernels)
     // per-variable plane pointers (filled by the launcher from rhs / q1 / qout + v*fstride): the

@@ -12,8 +12,8 @@
 //   m_mpi_proxy.fpp:490-499,592-601 (+y) pack / unpack       -> k_halo_pack / k_halo_unpack
 //   m_variables_conversion.fpp:313-375 cons -> prim          -> k_prim
 //   m_weno.fpp:470-535 + m_riemann_solvers.fpp:132-327 +
-//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_sweep_x (warp-shuffle pencil)
-//                                                               k_sweep_march (y / z pencils)
+//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_xrow (x: warp-shuffle pencil)
+//                                                               k_march3 (y / z: marching pencils)
 //   m_data_output.fpp:197-258 stability criteria             -> k_stability
 #pragma once
 #include <cuda_runtime.h>
@@ -384,170 +384,14 @@ __device__ __forceinline__ void store_visc_face(const SweepArgs &a, unsigned off
     a.visc_face[(ND + 1)*fs + off] = Re_avg[1];
 }
 
-// pointer to reconstruction variable v of the stage state: partial densities and volume
-// fractions come straight from the conservative state (q_prim_qp aliases q_cons_qp there,
-// m_rhs.fpp:154-164), velocity and pressure from the prim planes.
-template <int NF, int ND>
-__device__ __forceinline__ const double *var_plane(const SweepArgs &a, int v) {
-    constexpr int MOM = NF, ADV = NF + ND + 1;
-    return (v >= MOM && v < ADV) ? a.prim + (long long)(v - MOM)*a.g.fstride : a.q + (long long)v*a.g.fstride;
-}
-
 __device__ __forceinline__ void load_coef(const SweepArgs &a, int cell, double c[27]) {
     const double *p = a.coef + (cell - a.coef_lo);
 #pragma unroll
     for (int i = 0; i < 27; i++) c[i] = __ldg(p + (long long)i*a.clen);
 }
 
-// RHS of one cell from its two faces (m_rhs.fpp:567-589 / :610-635) and, if requested, the
-// fused RK stage (m_time_steppers.fpp:298-348).  Fm/ufm: face s-1/2, Fp/ufp: face s+1/2.
-template <int NF, int ND>
-__device__ __forceinline__ void finish_cell(const SweepArgs &a, long long cell, double rds,
-                                            const double *Fm, double ufm, const double *Fp, double ufp) {
-    constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1;
-    const long long fs = a.g.fstride;
-#pragma unroll
-    for (int v = 0; v < E; v++) {
-        double r = rds*(Fm[v] - Fp[v]);
-        if (!a.first_dir) r = a.rhs[v*fs + cell] + r;
-        double qs = 0.0;
-        if (v >= ADV || a.rk_mode >= 2) qs = a.q[v*fs + cell];
-        if (v >= ADV) r = r + rds*qs*(ufp - ufm);
-        if (a.rk_mode == 0) {
-            a.rhs[v*fs + cell] = r;
-        } else {
-            const double q1 = a.q1[v*fs + cell];
-            a.qout[v*fs + cell] = rk_apply(a.rk_mode, q1, qs, r, a.dt);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// x sweep.  One warp owns 32 consecutive cells j0-1 .. j0+30 of a row: every lane
-// reconstructs its own cell (all E variables), the right neighbour's left-face state arrives
-// by warp shuffle, the lane solves the Riemann problem at its right face, the left face's
-// flux arrives by shuffle, and lanes 1..30 finish their cell.  30 of 32 lanes produce output
-// (6 % redundancy), no shared memory, no block barrier, loads coalesced along x.
-// ------------------------------------------------------------------------------------------
-template <int NF, int ND>
-__global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1;
-    const GridDesc &g = a.g;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j0 = (blockIdx.x*4 + warp)*30;
-    if (j0 > g.N[0]) return;                       // whole warp out of range
-    const int j_raw = j0 - 1 + lane;
-    const int j = min(j_raw, g.N[0] + 1);          // clamp loads; clamped lanes never store
-    const int l = blockIdx.z;
-    double c[27];
-    load_coef(a, j, c);
-    const double rds = a.rds[j + g.b];
-    const unsigned full = 0xffffffffu;
-    for (int r = 0; r < a.rows; r++) {
-        const int k = blockIdx.y*a.rows + r;
-        if (k > g.N[1]) break;
-        const long long cell = g.at(j, k, l);
-        double vL[E], vR[E];
-#pragma unroll
-        for (int v = 0; v < E; v++) {
-            const double *p = var_plane<NF, ND>(a, v) + cell;
-            double s[5];
-#pragma unroll
-            for (int t = 0; t < 5; t++) s[t] = __ldg(p + (t - 2));
-            weno5(s, c, a.eps, vL[v], vR[v]);
-        }
-        // Riemann problem at face j+1/2: left state = my right-face value, right state = the
-        // next cell's left-face value (R-first call, m_rhs.fpp:545-556)
-        double Ls[E], Rs[E];
-#pragma unroll
-        for (int v = 0; v < E; v++) {
-            Ls[v] = vR[v];
-            Rs[v] = __shfl_down_sync(full, vL[v], 1);
-        }
-        if (a.bc_beg == -4 && j_raw == -1) {       // m_riemann_solvers.fpp:480-487
-#pragma unroll
-            for (int v = 0; v < E; v++) Ls[v] = Rs[v];
-        }
-        if (a.bc_end == -4 && j_raw == g.N[0]) {   // :515-523
-#pragma unroll
-            for (int v = 0; v < E; v++) Rs[v] = Ls[v];
-        }
-        double F[E], uf;
-        double vs[ND];
-        hllc<NF, ND, 0>(Ls, Rs, a.gammas, a.pi_infs, F, uf, vs);
-        double Fm[E], ufm;
-#pragma unroll
-        for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
-        ufm = __shfl_up_sync(full, uf, 1);
-        if (lane >= 1 && lane <= 30 && j_raw <= g.N[0])
-            finish_cell<NF, ND>(a, cell, rds, Fm, ufm, F, uf);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// y / z sweep.  Threads are laid along x (coalesced), each thread marches a pencil of `seg`
-// cells along the sweep direction, carrying the previous cell's right-face state and the
-// previous face's flux in registers: every reconstruction and every Riemann solve is done
-// exactly once per pencil (plus two warm-up reconstructions and one warm-up face).  The
-// 5-point stencil is re-read from L1/L2 each step; only HBM-resident planes are touched,
-// no transposed copy is ever made.
-// ------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR>
-__global__ void __launch_bounds__(128) k_sweep_march(const __grid_constant__ SweepArgs a) {
-    constexpr int E = 2*NF + ND + 1;
-    const GridDesc &g = a.g;
-    const int j = blockIdx.x*blockDim.x + threadIdx.x;
-    if (j > g.N[0]) return;
-    const int t = blockIdx.z;                      // the remaining transverse index
-    const int s0 = blockIdx.y*a.seg;
-    const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
-    const long long ss = DIR == 1 ? g.sy : g.sz;
-    const long long base = DIR == 1 ? g.at(j, 0, t) : g.at(j, t, 0);
-    double vRp[E], Fp[E], ufp = 0.0;
-#pragma unroll
-    for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
-    for (int s = s0 - 1; s <= s1 + 1; s++) {
-        double c[27];
-        load_coef(a, s, c);
-        const long long cell = base + (long long)s*ss;
-        double vL[E], vR[E];
-#pragma unroll
-        for (int v = 0; v < E; v++) {
-            const double *p = var_plane<NF, ND>(a, v) + cell;
-            double st[5];
-#pragma unroll
-            for (int q = 0; q < 5; q++) st[q] = __ldg(p + (long long)(q - 2)*ss);
-            weno5(st, c, a.eps, vL[v], vR[v]);
-        }
-        if (s >= s0) {
-            // face s-1/2 between cells s-1 (left state vRp) and s (right state vL)
-            double Ls[E], Rs[E];
-#pragma unroll
-            for (int v = 0; v < E; v++) { Ls[v] = vRp[v]; Rs[v] = vL[v]; }
-            if (a.bc_beg == -4 && s == 0) {
-#pragma unroll
-                for (int v = 0; v < E; v++) Ls[v] = Rs[v];
-            }
-            if (a.bc_end == -4 && s == g.N[DIR] + 1) {
-#pragma unroll
-                for (int v = 0; v < E; v++) Rs[v] = Ls[v];
-            }
-            double F[E], uf;
-            double vs[ND];
-            hllc<NF, ND, DIR>(Ls, Rs, a.gammas, a.pi_infs, F, uf, vs);
-            if (s >= s0 + 1)
-                finish_cell<NF, ND>(a, cell - ss, a.rds[s - 1 + g.b], Fp, ufp, F, uf);
-#pragma unroll
-            for (int v = 0; v < E; v++) Fp[v] = F[v];
-            ufp = uf;
-        }
-#pragma unroll
-        for (int v = 0; v < E; v++) vRp[v] = vR[v];
-    }
-}
-
 // ==========================================================================================
-// v2 sweep kernels: the stage state streams HBM -> shared memory through the TMA engine
+// Sweep kernels: the stage state streams HBM -> shared memory through the TMA engine
 // (cp.async.bulk, SASS UBLKCP) into a ring of row slots guarded by mbarriers; every value is
 // fetched from HBM exactly once per sweep, the conservative -> primitive conversion
 // (m_variables_conversion.fpp:326-373) happens in place in the ring (no q_prim planes in HBM,

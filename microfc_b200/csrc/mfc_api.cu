@@ -26,7 +26,7 @@ using namespace mfc;
 namespace {
 
 enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_RK, KC_PATCH, KC_COUNT };
-const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_sweep_x", "k_sweep_march<y>", "k_sweep_march<z>",
+const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_xrow", "k_march3<y>", "k_march3<z>",
                                       "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_rk", "k_patches"};
 
 // NCCL is resolved at run time so the library loads (and every symbol is exported) on hosts
@@ -84,7 +84,6 @@ struct Sim {
     int clen[3] = {0, 0, 0}, coef_lo[3] = {0, 0, 0};
     int coef_uniform[3] = {0, 0, 0};   // every cell of the direction has the same 27 coefficients (to 1e-12)
     double cuni[3][kNumWenoCoef];
-    int variant = 2;                   // sweep kernel generation (MFC_B200_KERNELS=1 selects the v1 kernels)
     double *rds[3] = {nullptr, nullptr, nullptr}, *ds[3] = {nullptr, nullptr, nullptr}, *cc[3] = {nullptr, nullptr, nullptr};
     double *rdcc[3] = {nullptr, nullptr, nullptr};   // 1/(s_cc(i+1) - s_cc(i)), viscous fast build
     // viscous runs: vel_src + Re_avg per face (nd+2 planes), dq_prim_d (nd*nd planes, weno_Re_flux)
@@ -325,7 +324,7 @@ int stab_reduce_and_copy() {
 int run_stability(const double *q, double dt) {
     int rc;
     // the v2 sweeps convert in shared memory; q_prim_vf is materialised only for this diagnostic
-    if (S.variant == 2 && (rc = run_prim(q))) return rc;
+    if ((rc = run_prim(q))) return rc;
     if ((rc = stab_reset())) return rc;
     StabArgs a{};
     a.g = S.g; a.q = q; a.prim = S.prim; a.dt = dt; a.out = S.stab_dev;
@@ -361,16 +360,16 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     if (stop && S.p.run_time_info && want_stab && S.last_q)
         if ((rc = run_stability(S.last_q, dt))) return rc;
     // m_rhs.fpp:435.  Anything that reads the whole ghosted box needs every direction complete.
-    const bool need_all = stop || S.variant != 2 || S.viscous;
+    const bool need_all = stop || S.viscous;
     if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
     // :445-447 (v2: fused into the sweeps; the viscous kernels read the velocity planes)
-    if ((S.variant != 2 || S.viscous) && (rc = run_prim(q))) return rc;
+    if (S.viscous && (rc = run_prim(q))) return rc;
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
     S.last_q = q;
     // m_time_steppers.fpp:288-290.  Inviscid fast build: the ICFL maximum is taken by the x sweep
     // itself from the primitive variables it already holds (no extra pass over the state).
     const bool do_stab = first_stage && S.p.run_time_info && want_stab;
-    const bool fuse_stab = do_stab && S.variant == 2 && !S.p.strict_math && !S.viscous;
+    const bool fuse_stab = do_stab && !S.p.strict_math && !S.viscous;
     if (do_stab && !fuse_stab) {
         if (!need_all)
             for (int d = 0; d < S.nd; d++)
@@ -407,7 +406,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
                 a.iRes[i][k] = k < S.Re_size[i] ? 1.0/S.Res[i][k] : 0.0;
             }
         }
-        a.variant = S.variant; a.coef_uniform = S.coef_uniform[d]; a.weno_order = S.p.weno_order;
+        a.coef_uniform = S.coef_uniform[d]; a.weno_order = S.p.weno_order;
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
@@ -561,12 +560,6 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     for (int i = 0; i < nf; i++)
         for (int k = 0; k < 2; k++)
             if (p->Re[i][k] > 0.0) { S.Re_idx[k][S.Re_size[k]] = i; S.Res[k][S.Re_size[k]] = p->Re[i][k]; S.Re_size[k]++; }
-    {
-        const char *e = std::getenv("MFC_B200_KERNELS");
-        S.variant = (e && e[0] == '1') ? 1 : 2;
-    }
-    if ((visc || p->weno_order != 5) && S.variant != 2)
-        return fail(MFC_B200_EUNSUPPORTED, "the v1 sweep kernels (MFC_B200_KERNELS=1) have no viscous / WENO1 / WENO3 path");
     S.g = make_grid(p->m, p->n, p->p, nd, S.b);
     if (S.g.fstride >= (1LL << 32)) return fail(MFC_B200_EUNSUPPORTED, "more than 2^32 elements per field (kernels use 32-bit in-plane offsets)");
     for (int d = 0; d < 3; d++)
@@ -678,7 +671,7 @@ int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
     for (auto &e : S.ev_halo) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     {
         const char *e = std::getenv("MFC_B200_OVERLAP");       // 0 disables (for A/B measurements)
-        S.overlap = S.variant == 2 && !S.viscous && !(e && e[0] == '0');
+        S.overlap = !S.viscous && !(e && e[0] == '0');
     }
     return 0;
 }

@@ -156,6 +156,8 @@ def test_call_order_is_enforced():
     assert L.mfc_b200_step(0, 1e-3, None, None) == -4
     assert L.mfc_b200_download(None) == -4
     assert b"before" in L.mfc_b200_last_error()
+    assert L.mfc_b200_generate_initial_condition(1, None, None, 1.0) == -4
+    assert b"before mfc_b200_init" in L.mfc_b200_last_error()
 
 
 @pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a host without a CUDA device")
