@@ -63,16 +63,15 @@ __device__ __forceinline__ double rcp_fast(double x) {
     r = fma(r, e, r);
     return r;
 }
-// sqrt(n/d) for n, d > 0 as n*rsqrt(n*d): one MUFU seed, two Newton steps, no division
+// sqrt(n/d) for n, d > 0 as n*rsqrt(n*d): one MUFU seed and one cubically convergent correction
+// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 (seed error ~2^-23 -> e^3), no division: 7 FP64 instructions
 __device__ __forceinline__ double sqrt_ratio_fast(double n, double d) {
     const double x = n*d;
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 5e-1*x;
-    double e = fma(-(h*y), y, 5e-1);
-    y = fma(y, e, y);
-    e = fma(-(h*y), y, 5e-1);
-    y = fma(y, e, y);
+    const double e = fma(-(x*y), y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    y = fma(y, p*e, y);
     return n*y;
 }
 
@@ -231,9 +230,11 @@ __device__ __forceinline__ void hllc(const double *L, const double *R, const dou
         v2L = fma(L[MOM + i], L[MOM + i], v2L);
         v2R = fma(R[MOM + i], R[MOM + i], v2R);
     }
-    double rho_L = 0.0, gamma_L = 0.0, pi_inf_L = 0.0, rho_R = 0.0, gamma_R = 0.0, pi_inf_R = 0.0;
+    // mixture rules (:159-167); the sums start from their first term instead of 0
+    double rho_L = L[0], gamma_L = L[ADV]*gam[0], pi_inf_L = L[ADV]*pinf[0];
+    double rho_R = R[0], gamma_R = R[ADV]*gam[0], pi_inf_R = R[ADV]*pinf[0];
 #pragma unroll
-    for (int i = 0; i < NF; i++) {
+    for (int i = 1; i < NF; i++) {
         rho_L = rho_L + L[i];
         gamma_L = fma(L[ADV + i], gam[i], gamma_L);
         pi_inf_L = fma(L[ADV + i], pinf[i], pi_inf_L);
@@ -248,14 +249,14 @@ __device__ __forceinline__ void hllc(const double *L, const double *R, const dou
     const double s_L = fmin(uL - c_L, uR - c_R);
     const double s_R = fmax(uR + c_R, uL + c_L);
     const double mL = rho_L*(s_L - uL), mR = rho_R*(s_R - uR);
-    const double s_S = (pres_R - pres_L + mL*uL - mR*uR)*rcp_fast(mL - mR);
+    const double s_S = (pres_R - pres_L + mL*uL - mR*uR)*rcp_fast3(mL - mR);
     const bool left = !signbit(s_S);                     // xi_M = 1 (:254)
     const double rho = left ? rho_L : rho_R, u = left ? uL : uR, pres = left ? pres_L : pres_R;
     const double s_K = left ? s_L : s_R;
     const double s_MP = left ? fmin(0.0, s_L) : fmax(0.0, s_R);
     const double E_K = fma(left ? gamma_L : gamma_R, pres, left ? pi_inf_L : pi_inf_R) + 5e-1*rho*(left ? v2L : v2R);
     const double da = s_K - s_S, db = s_K - u;
-    const double rab = rcp_fast(da*db);
+    const double rab = rcp_fast3(da*db);
     const double xi = db*db*rab;                         // (s_K - u_K)/(s_K - s_S)
     const double p_over = pres*da*rab;                   // p_K/(s_K - u_K)
     const double w = fma(s_MP, xi - 1.0, u);             // u_K + s_MP (xi_K - 1)
@@ -476,6 +477,7 @@ __host__ __device__ constexpr int march_slots(int dir, int nd) { return march_ri
 template <int NF, int ND, int LD>
 __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, const double *pinf) {
     constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+#if MFC_STRICT
     double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
 #pragma unroll
     for (int i = 0; i < NF; i++) {
@@ -484,6 +486,16 @@ __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, 
         gamma = gamma + al*gam[i];
         pi_inf = pi_inf + al*pinf[i];
     }
+#else
+    double rho = cellp[0], gamma = cellp[ADV*LD]*gam[0], pi_inf = cellp[ADV*LD]*pinf[0];
+#pragma unroll
+    for (int i = 1; i < NF; i++) {
+        const double al = cellp[(ADV + i)*LD];
+        rho = rho + cellp[i*LD];
+        gamma = fma(al, gam[i], gamma);
+        pi_inf = fma(al, pinf[i], pi_inf);
+    }
+#endif
     rho = fmax(rho, 1e-16);
     double dyn = 0.0;
 #if MFC_STRICT
@@ -496,7 +508,7 @@ __device__ __forceinline__ void prim_in_place(double *cellp, const double *gam, 
     }
     cellp[EN*LD] = (cellp[EN*LD] - dyn - pi_inf)/gamma;
 #else
-    const double ir = rcp_fast(rho), ig = rcp_fast(gamma);
+    const double ir = rcp_fast3(rho), ig = rcp_fast3(gamma);
 #pragma unroll
     for (int i = 0; i < ND; i++) {
         const double mom = cellp[(MOM + i)*LD];
@@ -613,11 +625,15 @@ __device__ __forceinline__ void finish_vals(const SweepArgs &a, double rds, cons
     }
 #else
     // stage state rebuilt from the ring
-    double qs[E], rho = 0.0, gamma = 0.0, pi_inf = 0.0, v2 = 0.0;
+    double qs[E], v2 = 0.0;
 #pragma unroll
     for (int i = 0; i < NF; i++) {
         qs[i] = pc[i*LD];
         qs[ADV + i] = al[i];
+    }
+    double rho = qs[0], gamma = al[0]*a.gammas[0], pi_inf = al[0]*a.pi_infs[0];
+#pragma unroll
+    for (int i = 1; i < NF; i++) {
         rho += qs[i];
         gamma = fma(al[i], a.gammas[i], gamma);
         pi_inf = fma(al[i], a.pi_infs[i], pi_inf);
@@ -718,11 +734,21 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 
     int slot = 0;
     unsigned phase = 0;
+    static_assert(kWX - 32 == 8 && R >= 3, "the pass over columns 32..39 serves two rows with 16 lanes");
     for (int r = 0; r < nrows; r++, off += usy) {
         double *row = ring + slot*SLOT;
-        mbar_wait(&bar[slot], phase);
+        // Conversion.  The warp stages 40 columns: one pass of 32 lanes per row, plus a second pass
+        // for columns 32..39 that would keep only 8 lanes busy -- it is run every OTHER row, for
+        // this row and the next one (requested three rows ago, so it has arrived) with 16 lanes.
+        const bool even = (r & 1) == 0, has_next = r + 1 < nrows;
+        const int sn = slot + 1 == R ? 0 : slot + 1;
+        if (even) {                                    // odd rows arrived (and had columns 32..39 done) one row ago
+            mbar_wait(&bar[slot], phase);
+            if (has_next) mbar_wait(&bar[sn], sn == 0 ? phase ^ 1u : phase);
+        }
         prim_in_place<NF, ND, kWX>(row + lane, a.gammas, a.pi_infs);
-        if (lane < kWX - 32) prim_in_place<NF, ND, kWX>(row + lane + 32, a.gammas, a.pi_infs);
+        if (even && lane < 16 && (lane < 8 || has_next))
+            prim_in_place<NF, ND, kWX>((lane < 8 ? row : ring + sn*SLOT) + 32 + (lane & 7), a.gammas, a.pi_infs);
         __syncwarp();
         CellIn<E, ACC, RK> in;
         if (RK) load_cell<NF, ND, ACC, RK>(a, off, in);
@@ -740,9 +766,9 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
         for (int v = 0; v < E; v++) pc[v] = (RK || v >= ADV || stab_on) ? p[v*kWX] : 0.0;
 #if !MFC_STRICT
         if (stab_on) {                                 // ICFL, m_data_output.fpp:215-233 (inviscid)
-            double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
+            double rho = pc[0], gamma = pc[ADV]*a.gammas[0], pi_inf = pc[ADV]*a.pi_infs[0];
 #pragma unroll
-            for (int i = 0; i < NF; i++) {
+            for (int i = 1; i < NF; i++) {
                 rho += pc[i];
                 gamma = fma(pc[ADV + i], a.gammas[i], gamma);
                 pi_inf = fma(pc[ADV + i], a.pi_infs[i], pi_inf);
