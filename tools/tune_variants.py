@@ -15,10 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     # name: (RING_Y, WARPS_Y, CTAS_Y, RING_X, WARPS_X, CTAS_X, extra -D flags)
     # (v4: k_march3 adds 2-3 operand / output slots per warp to RING_Y / RING_Z; 72 KB per CTA at 3 CTAs)
-    "base": (7, 4, 3, 4, 4, 5, ""),
-    "y8": (8, 4, 3, 4, 4, 5, ""),
-    "x4": (7, 4, 3, 4, 4, 4, ""),
-    "x3r3c6": (7, 4, 3, 3, 4, 6, ""),
+    "x_r3c6": (7, 4, 3, 3, 4, 6, ""),
+    "x_r3c7": (7, 4, 3, 3, 4, 7, ""),
 }
 
 
