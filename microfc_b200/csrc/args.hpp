@@ -40,7 +40,7 @@ struct SweepArgs {
     int coef_uniform;      // 1: cuni[] holds the coefficients of every cell of this direction
     double cuni[kNumWenoCoef];   // uniform-grid WENO coefficients (COEF = 0 kernels)
     // per-variable plane pointers (filled by the launcher from rhs / q1 / qout + v*fstride): the
-    // v2 kernels address a cell as plane pointer (constant bank) + 32-bit element offset, one
+    // sweep kernels address a cell as plane pointer (constant bank) + 32-bit element offset, one
     // IMAD.WIDE per access instead of 64-bit pointer arithmetic per variable
     const double *q_v[kMaxE], *rhs_v[kMaxE], *q1_v[kMaxE];
     double *rhsw_v[kMaxE], *qout_v[kMaxE];
@@ -80,20 +80,11 @@ struct ViscArgs {
     // i = -b .. N+b-1, and of the cell widths
     const double *rdcc[3], *rds[3];
     // last direction: the TVD-RK statement rk_mode (1..4, 0 = store the RHS) is applied here
-    // instead of by a separate k_rk pass; E variables, q1 = q_cons_ts(1), qs = stage state
+    // instead of by a separate pass; E variables, q1 = q_cons_ts(1), qs = stage state
     int rk_mode, E;
     const double *q1, *qs;
     double *qout;
     double dt;
-};
-
-// the TVD-RK statement as a separate pass (viscous runs, where it cannot be fused into the sweep)
-struct RkArgs {
-    GridDesc g;
-    const double *q1, *qs, *rhs;
-    double *qout;
-    double dt;
-    int rk_mode, E;
 };
 
 struct BcArgs {
@@ -169,7 +160,6 @@ struct Launchers {
     int (*stability)(int nf, int nd, const StabArgs &, cudaStream_t);
     int (*visc_grad)(int nd, const ViscArgs &, cudaStream_t);
     int (*visc)(int nd, const ViscArgs &, cudaStream_t);
-    int (*rk)(const RkArgs &, cudaStream_t);
 };
 const Launchers &launchers_fast();
 const Launchers &launchers_strict();

@@ -681,11 +681,13 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
 }
 
 // ------------------------------------------------------------------------------------------
-// x sweep, v2.  Every WARP is an independent pipeline: it owns 30 consecutive cells of a row
-// and streams `rows` consecutive rows through its private 4-slot ring (one 320-byte bulk copy
-// per variable and row, issued by lane 0 three rows ahead of the compute; mbarrier per slot).
-// No block-wide barrier exists, so warps never wait for each other.  Within a row the work is
-// the warp-shuffle pencil of v1: lane = cell, neighbours' face states / fluxes by shuffle.
+// x sweep.  Every WARP is an independent pipeline: it owns 30 consecutive cells of a row
+// and streams `rows` consecutive rows through its private 4-slot ring (one tensor-map bulk
+// copy of 40 columns x E variables per row, issued by lane 0 three rows ahead of the compute;
+// mbarrier per slot).  No block-wide barrier exists, so warps never wait for each other.
+// Within a row: lane = cell; every lane reconstructs its own cell (all E variables), the right
+// neighbour's left-face state arrives by warp shuffle, the lane solves the Riemann problem at
+// its right face, the left face's flux arrives by shuffle, and lanes 1..30 finish their cell.
 // BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).  VISC: viscous run,
 // vel_src and Re_avg of every face are stored for k_visc.
 // ------------------------------------------------------------------------------------------
@@ -830,8 +832,8 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
 //         written back with one bulk tensor store; the interior-clipped tensor map drops the
 //         columns beyond the domain, so there are no masked per-lane stores
 // Each operand row is requested one march iteration (~3 us) before it is read, so the warp
-// never waits on a global load (v3a: 8-11 % of all issue-stall samples sat on the first use of
-// an LDG'd operand, profiles/r01_v3a_stalls.md), and the 16 LDG/STG + 48 address instructions
+// never waits on a global load (with LDG operands 8-11 % of all issue-stall samples sat on their
+// first use, profiles/r01_v3a_stalls.md), and the 16 LDG/STG + 48 address instructions
 // per cell become 24 LDS/STS.  The only synchronisation is the mbarrier wait and a __syncwarp
 // before a slot is handed back.  Lanes beyond the domain compute on zero-filled columns.
 // ------------------------------------------------------------------------------------------
@@ -1373,17 +1375,5 @@ __global__ void __launch_bounds__(128, 4) k_visc(const __grid_constant__ ViscArg
 }
 #undef VDIV
 #undef VDIV3
-
-// the TVD-RK statement on its own (m_time_steppers.fpp:167,245,322,342), interior cells only
-__global__ void __launch_bounds__(256) k_rk(const __grid_constant__ RkArgs a) {
-    const GridDesc &g = a.g;
-    const int j = blockIdx.x*blockDim.x + threadIdx.x;
-    if (j > g.N[0]) return;
-    const long long cell = g.at(j, blockIdx.y, blockIdx.z), fs = g.fstride;
-    for (int v = 0; v < a.E; v++) {
-        const long long o = v*fs + cell;
-        a.qout[o] = rk_apply(a.rk_mode, a.q1[o], a.qs[o], a.rhs[o], a.dt);
-    }
-}
 
 }  // namespace MFC_NS

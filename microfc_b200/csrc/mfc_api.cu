@@ -25,9 +25,9 @@ using namespace mfc;
 
 namespace {
 
-enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_RK, KC_PATCH, KC_COUNT };
+enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_PATCH, KC_COUNT };
 const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_xrow", "k_march3<y>", "k_march3<z>",
-                                      "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_rk", "k_patches"};
+                                      "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_patches"};
 
 // NCCL is resolved at run time so the library loads (and every symbol is exported) on hosts
 // without it; only mfc_b200_comm_init needs it.  In a process that already imported torch
@@ -249,9 +249,9 @@ int physical_bc_dir(double *q, int d) {
 }
 
 // Ghost fill of the stage state, m_rhs.fpp:686-908.
-//   sequential (single rank, viscous, v1 kernels): one direction after the other on the compute
+//   sequential (single rank, viscous): one direction after the other on the compute
 //     stream, later directions covering the ghosts of the earlier ones (corners), like the reference.
-//   overlapped (multi-rank inviscid v2 path): a sweep along d reads ghosts of direction d only,
+//   overlapped (multi-rank inviscid): a sweep along d reads ghosts of direction d only,
 //     at interior transverse indices -- corner ghosts are never read -- so the three exchanges
 //     are independent.  They are enqueued on the communication stream in the order x, y, z; the
 //     sweep along d waits for exchange d only (ghosts_ready), i.e. the y and z exchanges run
@@ -323,7 +323,7 @@ int stab_reduce_and_copy() {
 }
 int run_stability(const double *q, double dt) {
     int rc;
-    // the v2 sweeps convert in shared memory; q_prim_vf is materialised only for this diagnostic
+    // the sweeps convert in shared memory; q_prim_vf is materialised only for this diagnostic
     if ((rc = run_prim(q))) return rc;
     if ((rc = stab_reset())) return rc;
     StabArgs a{};
@@ -362,7 +362,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     // m_rhs.fpp:435.  Anything that reads the whole ghosted box needs every direction complete.
     const bool need_all = stop || S.viscous;
     if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
-    // :445-447 (v2: fused into the sweeps; the viscous kernels read the velocity planes)
+    // :445-447 (fused into the sweeps; the viscous kernels read the velocity planes)
     if (S.viscous && (rc = run_prim(q))) return rc;
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
     S.last_q = q;
