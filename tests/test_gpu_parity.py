@@ -21,6 +21,9 @@ CASES = {
     "shockdroplet_2d_inviscid": lambda: cases.shockdroplet_2d(Nx=199, Ny=59),
     "shearlayer_2d_periodic": lambda: cases.shearlayer_2d(Nx=79, Ny=39),
     "shockbubble_3d": lambda: cases.shockbubble_3d(nc=32),
+    # 3-D with partly filled warps / tiles in every direction and a periodic direction
+    "shockbubble_3d_odd_sizes": lambda: cases.shockbubble_3d(ncx=50, ncy=37, ncz=29),
+    "shockbubble_3d_periodic_z": lambda: cases.shockbubble_3d(nc=32, periodic_z=True),
     # viscous source flux: WENO-reconstructed gradients / finite differences
     "viscous_2d_weno": lambda: cases.viscous_2d(N=49, weno_Re_flux=True),
     "viscous_2d_fd": lambda: cases.viscous_2d(N=49, weno_Re_flux=False),
