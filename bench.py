@@ -9,7 +9,7 @@ HLLC sweeps with the update fused into the last sweep, plus the ICFL diagnostic)
 workload BASELINE.json's target names: the synthetic 3-D two-fluid shock-bubble at 512^3 cells
 PER GPU (configs[4]), weak-scaled over N GPUs with the reference's block decomposition and an
 NCCL halo exchange.  Other BASELINE configs: --workload advection_2d_1024 | shockbubble_2d_4096 |
-shockdroplet_2d_viscous_2048.
+shockdroplet_2d_viscous_2048 | sod_1d_400.
 
 Printed JSON (rank 0, one line):
   value      Mcell-steps/s of the whole job, state resident in HBM, timed with CUDA events on
@@ -88,6 +88,12 @@ def workload_case(name: str, n_gpus: int, cells: int | None):
         d = cases.advection_2d(N=nc * px - 1, Nt=10 ** 6)
         d['n'] = nc * py - 1
         desc = f"examples/2D_advection at {nc}^2 cells per GPU (BASELINE configs[1])"
+    elif name == "sod_1d_400":
+        nc = cells or 400
+        d = cases.sod_1d(Nx=nc * n_gpus - 1, Nt=10 ** 6)
+        d['dt'] = d['dt'] * 400.0 / nc
+        px, py, pz = n_gpus, 1, 1
+        desc = f"examples/1D_sodshocktube, {nc} cells per GPU (BASELINE configs[0], the reference's own CPU-runnable case)"
     elif name == "shockdroplet_2d_viscous_2048":
         nc = cells or 2048
         d = cases.shockdroplet_2d(Nx=nc * px - 1, Ny=nc * py - 1, Nt=10 ** 6, viscous=True)
@@ -156,6 +162,9 @@ def cpu_reference_run(cfg_full: CaseConfig, steps: int, warmup: int, sample_cell
     if nd == 3:
         d = cases.shockbubble_3d(nc=sample_cells, Nt=10 ** 6)
         sample = f"{sample_cells}^3 cells of the same 3-D shock-bubble case"
+    elif nd == 1:
+        d = cases.sod_1d(Nx=sample_cells - 1, Nt=10 ** 6)
+        sample = f"{sample_cells} cells of the same 1-D case"
     else:
         if cfg_full.viscous:
             d = cases.shockdroplet_2d(Nx=sample_cells - 1, Ny=sample_cells - 1, Nt=10 ** 6, viscous=True)
@@ -211,7 +220,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = args.cpu_sample_cells or (128 if nd == 3 else 1024)
+        sample = args.cpu_sample_cells or {3: 128, 2: 1024, 1: 400}[nd]
         r = cpu_reference_run(cfg, K, W, sample)
         line = {"impl": "reference", "metric": "Mcell-steps/s", "value": r["value"], "unit": "Mcell-steps/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -344,7 +353,7 @@ def main():
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample_cells or (128 if nd == 3 else 1024)
+        sample = args.cpu_sample_cells or {3: 128, 2: 1024, 1: 400}[nd]
         r = cpu_reference_run(cfg, 3, 1, sample)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
