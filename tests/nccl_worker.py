@@ -24,6 +24,10 @@ CASES = {
     "shearlayer_2d": (lambda: cases.shearlayer_2d(Nx=79, Ny=63), 25),          # periodic in x
     "shockdroplet_2d": (lambda: cases.shockdroplet_2d(Nx=199, Ny=59), 20),      # reflective y
     "shockbubble_3d": (lambda: cases.shockbubble_3d(nc=52), 6),
+    # >= 246 cells per rank along x: the x sweep is launched in two parts (tiles that read no x
+    # ghost column while the x halo is in flight, then the boundary tiles)
+    "shockbubble_2d_wide": (lambda: cases.shockbubble_2d_cells(512, 64), 20),
+    "shockbubble_3d_wide": (lambda: cases.shockbubble_3d(ncx=512, ncy=26, ncz=26), 4),
     # viscous: buff_size 6 and corner ghosts (y messages span the x ghosts, m_mpi_proxy.fpp:736-739)
     "viscous_2d": (lambda: cases.viscous_2d(N=63, weno_Re_flux=True), 10),
     "shockdroplet_2d_viscous": (lambda: cases.shockdroplet_2d(Nx=199, Ny=59, viscous=True), 20),

@@ -29,7 +29,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("nproc,names", [(2, ["sod_1d", "shockbubble_2d", "shearlayer_2d", "shockdroplet_2d", "shockbubble_3d", "viscous_2d",
-                                              "shockdroplet_2d_viscous"]),
+                                              "shockdroplet_2d_viscous", "shockbubble_2d_wide", "shockbubble_3d_wide"]),
                                          (4, ["shockbubble_2d", "shearlayer_2d", "shockbubble_3d", "viscous_2d", "shockdroplet_2d_viscous"]),
                                          (8, ["shockbubble_3d"])])
 def test_nccl_halo_exchange_matches_single_rank_oracle(nproc, names):
