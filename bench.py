@@ -149,7 +149,14 @@ def measured_peaks():
             hbm, src = float(json.load(open(p))["hbm_gbs"]), "measured"
         except Exception:
             pass
-    fp64, fsrc = FP64_PEAK_TFLOPS_FALLBACK, "measured (tools/fp64_peak.cu on this pool, profiles/r01_fp64_peak.json)"
+    fp64, fsrc = FP64_PEAK_TFLOPS_FALLBACK, "fallback (earlier measurement on this pool)"
+    fp = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+    if os.path.exists(fp):
+        try:
+            fp64 = float(json.load(open(fp))["fp64_dfma_tflops_sustained"])
+            fsrc = "measured (tools/fp64_peak.cu on this pool, profiles/r01_fp64_peak.json)"
+        except Exception:
+            pass
     return hbm, src, fp64, fsrc
 
 
