@@ -734,24 +734,30 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
     unsigned off = (unsigned)g.at(min(j, g.N[0]), k0, l);
     const unsigned usy = (unsigned)g.sy;
 
-    int slot = 0;
-    unsigned phase = 0;
+    // Conversion runs ONE ROW AHEAD of the reconstruction, so that its dependent chain (LDS ->
+    // reciprocals -> STS) overlaps the register-only Riemann solve of the current row instead of
+    // standing in front of the reconstruction.  The warp stages 40 columns: a pass of 32 lanes
+    // per row (placed next to hllc below) plus a pass for columns 32..39 that would keep only 8
+    // lanes busy -- it serves two rows at once, every other row, with 16 lanes.
     static_assert(kWX - 32 == 8 && R >= 3, "the pass over columns 32..39 serves two rows with 16 lanes");
+    mbar_wait(&bar[0], 0);                             // rows 0 and 1: arrival, row 0 fully converted
+    if (nrows > 1) mbar_wait(&bar[1], 0);
+    prim_in_place<NF, ND, kWX>(ring + lane, a.gammas, a.pi_infs);
+    if (lane < 16 && (lane < 8 || nrows > 1))
+        prim_in_place<NF, ND, kWX>((lane < 8 ? ring : ring + SLOT) + 32 + (lane & 7), a.gammas, a.pi_infs);
+    __syncwarp();
+    int slot = 0;
     for (int r = 0; r < nrows; r++, off += usy) {
         double *row = ring + slot*SLOT;
-        // Conversion.  The warp stages 40 columns: one pass of 32 lanes per row, plus a second pass
-        // for columns 32..39 that would keep only 8 lanes busy -- it is run every OTHER row, for
-        // this row and the next one (requested three rows ago, so it has arrived) with 16 lanes.
-        const bool even = (r & 1) == 0, has_next = r + 1 < nrows;
-        const int sn = slot + 1 == R ? 0 : slot + 1;
-        if (even) {                                    // odd rows arrived (and had columns 32..39 done) one row ago
-            mbar_wait(&bar[slot], phase);
-            if (has_next) mbar_wait(&bar[sn], sn == 0 ? phase ^ 1u : phase);
+        const int ka = r + 1, sa = ka % R;             // the row converted in this iteration
+        double *rowa = ring + sa*SLOT;
+        if ((ka & 1) == 0 && ka < nrows) {             // pair (ka, ka+1): arrival + the pass over columns 32..39
+            const int kb = ka + 1, sb = kb % R;
+            mbar_wait(&bar[sa], (unsigned)(ka/R) & 1u);
+            if (kb < nrows) mbar_wait(&bar[sb], (unsigned)(kb/R) & 1u);
+            if (lane < 16 && (lane < 8 || kb < nrows))
+                prim_in_place<NF, ND, kWX>((lane < 8 ? rowa : ring + sb*SLOT) + 32 + (lane & 7), a.gammas, a.pi_infs);
         }
-        prim_in_place<NF, ND, kWX>(row + lane, a.gammas, a.pi_infs);
-        if (even && lane < 16 && (lane < 8 || has_next))
-            prim_in_place<NF, ND, kWX>((lane < 8 ? row : ring + sn*SLOT) + 32 + (lane & 7), a.gammas, a.pi_infs);
-        __syncwarp();
         CellIn<E, ACC, RK> in;
         if (RK) load_cell<NF, ND, ACC, RK>(a, off, in);
         const double *p = row + sx;
@@ -786,7 +792,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
         fence_proxy_async();
         __syncwarp();                                  // the warp is done with this slot
         if (lane == 0 && r + R < nrows) issue(r + R, slot);
-        if (++slot == R) { slot = 0; phase ^= 1u; }
+        if (++slot == R) slot = 0;
         double Rs[E];
 #pragma unroll
         for (int v = 0; v < E; v++) Rs[v] = __shfl_down_sync(full, vL[v], 1);
@@ -802,6 +808,9 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
         }
         double F[E], uf;
         double vs[ND];
+        // columns 0..31 of the NEXT row (arrived: see the pair wait above / the prologue); past the
+        // last row this converts an idle slot, harmlessly
+        prim_in_place<NF, ND, kWX>(rowa + lane, a.gammas, a.pi_infs);
         hllc<NF, ND, 0>(vR, Rs, a.gammas, a.pi_infs, F, uf, vs);
         if (VISC && lane <= kWarpCells && j_raw <= g.N[0])   // faces -1/2 .. N+1/2, keyed by the left cell
             store_visc_face<NF, ND>(a, off, vR, Rs, vs);
@@ -810,6 +819,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
         for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
         ufm = __shfl_up_sync(full, uf, 1);
         finish_cell2<NF, ND, 1, ACC, RK>(a, off, store_on, rds, pc, in, Fm, ufm, F, uf);
+        __syncwarp();                                  // the next row is converted for every lane
     }
     if (stab_on) {                                     // all values >= 0: the bit pattern orders like the value
         unsigned long long b = (unsigned long long)__double_as_longlong(icfl);
@@ -860,7 +870,13 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
     const int s1 = min(s0 + a.seg - 1, g.N[DIR]);
     const long long ss = DIR == 1 ? g.sy : g.sz;
     const long long base = DIR == 1 ? g.at(j0, 0, t) : g.at(j0, t, 0);   // row 0 of the warp's columns
-    const int r_first = s0 - 3, r_last = s1 + 3;       // rows s0-3 .. s1+3
+    // AHEAD (rings of >= 7 rows): the conversion runs one row ahead of the reconstruction -- row
+    // s+3 is converted in iteration s, next to the register-only Riemann solve, so that its
+    // dependent chain (LDS -> reciprocals -> STS) does not stand in front of the reconstruction.
+    // One extra row (s1+4: at most the outermost ghost row, or zero-filled beyond it) is streamed
+    // so that the conversion needs no guard.
+    constexpr bool AHEAD = R >= 7;
+    const int r_first = s0 - 3, r_last = s1 + 3 + (AHEAD ? 1 : 0);       // rows s0-3 .. s1+3 (+1)
     const bool need_q1 = RK && (MFC_STRICT ? a.rk_mode != 0 : a.rk_mode >= 2);
     if (lane == 0) {
         for (int i = 0; i < NB; i++) mbar_init(&bar[i], 1);
@@ -888,7 +904,7 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
     int slot_cv = 0, slot_lo = 0;
     unsigned phase_cv = 0, phase_op = 0;
 #pragma unroll 1
-    for (int i = 0; i < 4; i++) {                      // rows s0-3 .. s0
+    for (int i = 0; i < 4 + (AHEAD ? 1 : 0); i++) {    // rows s0-3 .. s0 (+ s0+1)
         mbar_wait(&bar[slot_cv], phase_cv);
         prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
         if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
@@ -908,9 +924,10 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
     // right-face state of cell s-1, finish cell s-1 with the carried flux of face s-3/2.
 #pragma unroll 1
     for (int s = s0 - 1; s <= s1 + 1; s++) {
-        mbar_wait(&bar[slot_cv], phase_cv);            // row s+2
-        prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
+        mbar_wait(&bar[slot_cv], phase_cv);            // row s+2 (AHEAD: s+3) has arrived
+        double *const row_cv = ring + slot_cv*SLOT + lane;
         if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
+        if (!AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
         off += uss;
         weno.load(a, s);
         double vL[E], vRn[E];
@@ -920,7 +937,8 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
             weno(st, vL[v], vRn[v]);
         }
         const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
-        if (s >= s0) {
+        {   // face s-1/2.  The warm-up iteration s0-1 solves it too (against the zero state; the
+            // result is overwritten before any use): one straight-line body, no second copy
             double Fn[E], ufn;
             CellIn<E, ACC, RK> in;
             if (fin) {                                 // operand rows requested one iteration ago
@@ -956,8 +974,9 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
             }
             const double *L = BC4 ? Ls : vRp;
             double vs[ND];
+            if (AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
             hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Fn, ufn, vs);
-            if (VISC && on) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
+            if (VISC && on && s >= s0) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
             if (fin) {
                 double y[E];
                 finish_vals<NF, ND, kWY, ACC, RK>(a, a.rds[s - 1 + g.b], p1, in, Fp, ufp, Fn, ufn, y);   // p1: row s-1
