@@ -175,6 +175,7 @@ def cpu_reference_run(cfg_full: CaseConfig, steps: int, warmup: int, sample_cell
     else:
         if cfg_full.viscous:
             d = cases.shockdroplet_2d(Nx=sample_cells - 1, Ny=sample_cells - 1, Nt=10 ** 6, viscous=True)
+            d['dt'] = d['dt'] * min(1.0, 0.037 / 0.25)       # same rule as the GPU workload: dt from the smaller width
         elif cfg_full.bc[0][0] == -6:
             d = cases.shockbubble_2d_cells(sample_cells, sample_cells, Nt=10 ** 6)
         else:

@@ -1,0 +1,72 @@
+"""bench.py's contract with the driver, as far as it can be checked without a GPU: the reference
+arm (`--impl reference`, the CPU restatement under oracle/) prints exactly ONE JSON line on
+stdout with the agreed keys; under torchrun only rank 0 prints; and the CUDA arm FAILS LOUDLY
+on a host without a device (no CPU fallback, nothing on stdout)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, cwd=ROOT,
+                          env=e, timeout=600)
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--cpu-sample-cells", "32"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference"
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["metric"] == "Mcell-steps/s" and j["unit"] == "Mcell-steps/s" and j["higher_is_better"] is True
+    assert j["steps"] == 2 and j["warmup"] == 1 and j["n_gpus"] == 1 and j["vs_baseline"] is None
+    assert j["dtype"] == "f64" and j["data"] == "synthetic" and j["scaling"] == "weak"
+    assert "workload" in j["config"] and "512^3" in j["config"]["workload"]
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "32^3" in cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["value"] > 0
+
+
+def test_reference_arm_only_rank_zero_prints_under_torchrun():
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-sample-cells", "32"],
+             env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("workload", ["advection_2d_1024", "shockbubble_2d_4096", "shockdroplet_2d_viscous_2048", "sod_1d_400"])
+def test_reference_arm_covers_every_baseline_workload(workload):
+    # (the shipped patches need >= ~100 cells per direction to be resolved at all -- the oracle
+    # itself goes non-finite below that -- and the thin shock-droplet domain ~1000)
+    sample = "1024" if "droplet" in workload else "128"
+    r = _run(["--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0", "--cpu-sample-cells", sample])
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads(r.stdout.strip())
+    assert j["value"] > 0 and j["config"]["num_dims"] in (1, 2)
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a host without a CUDA device")
+def test_cuda_arm_fails_loudly_without_a_device():
+    r = _run(["--gpus", "1", "--steps", "1", "--warmup", "0", "--cells", "32", "--no-cpu-baseline"])
+    assert r.returncode != 0
+    assert r.stdout.strip() == ""
+    assert "no CPU fallback" in r.stderr or "MfcB200Error" in r.stderr or "CUDA" in r.stderr
