@@ -34,6 +34,41 @@ from .case import CaseConfig
 from .domain import RankLayout, ghosted_metrics, rank_layout
 
 
+def patch_array(cfg: CaseConfig):
+    """patch_icpp(1:num_patches) of the case as the ``mfc_b200_patch_t`` array of the C ABI."""
+    n = cfg.num_patches
+    if not 1 <= n <= abi.MAX_PATCHES:
+        raise ValueError("num_patches must be 1..%d" % abi.MAX_PATCHES)
+    arr = (abi.Patch * n)()
+    for i, pt in enumerate(cfg.patches):
+        c = arr[i]
+        c.geometry, c.smoothen, c.smooth_patch_id = pt.geometry, int(pt.smoothen), pt.smooth_patch_id
+        for k in range(abi.MAX_PATCHES + 1):
+            c.alter_patch[k] = int(bool(pt.alter_patch.get(k, False))) if k <= n else 0
+        c.x_centroid, c.y_centroid, c.z_centroid = pt.x_centroid, pt.y_centroid, pt.z_centroid
+        c.length_x, c.length_y, c.length_z = pt.length_x, pt.length_y, pt.length_z
+        c.radius, c.epsilon, c.smooth_coeff, c.pres = pt.radius, pt.epsilon, pt.smooth_coeff, pt.pres
+        for k in range(3):
+            c.radii[k], c.normal[k], c.vel[k] = pt.radii[k], pt.normal[k], pt.vel[k]
+        for k in range(abi.MAX_FLUIDS):
+            c.alpha_rho[k], c.alpha[k] = pt.alpha_rho[k], pt.alpha[k]
+    return arr
+
+
+def rank_cell_centres(cfg: CaseConfig, lay: RankLayout, cb_glb: List[np.ndarray]):
+    """pre_process' cell centres (x_cb(i-1) + x_cb(i))/2 (m_start_up.fpp:717,743) of one rank's
+    interior cells, per active direction, and the GLOBAL minimum cell width (s_mpi_reduce_min,
+    :720) -- what ``mfc_b200_generate_initial_condition`` takes besides the patches."""
+    zs, ys, xs = lay.interior_slices()
+    sl = (xs, ys, zs)
+    cc, dmin = [], []
+    for d in range(cfg.num_dims):
+        cb = cb_glb[d]
+        cc.append(np.ascontiguousarray(((cb[1:] + cb[:-1]) / 2.0)[sl[d]]))
+        dmin.append(float(np.min(cb[1:] - cb[:-1])))
+    return cc, min(dmin)
+
+
 class Simulation:
     def __init__(self, cfg: CaseConfig, cb_glb: List[np.ndarray], rank: int = 0, num_procs: int = 1,
                  strict: bool = False, device: int = -1, unique_id: Optional[bytes] = None,
@@ -120,35 +155,12 @@ class Simulation:
         what pre_process itself derives from the grid files: its cell centres
         ``(x_cb(i-1) + x_cb(i))/2`` (m_start_up.fpp:717,743) for this rank's cells and the global
         minimum cell width (s_mpi_reduce_min, :720)."""
-        cfg, lay = self.cfg, self.layout
-        nd = cfg.num_dims
-        n = cfg.num_patches
-        if not 1 <= n <= abi.MAX_PATCHES:
-            raise ValueError("num_patches must be 1..%d" % abi.MAX_PATCHES)
-        arr = (abi.Patch * n)()
-        for i, pt in enumerate(cfg.patches):
-            c = arr[i]
-            c.geometry, c.smoothen, c.smooth_patch_id = pt.geometry, int(pt.smoothen), pt.smooth_patch_id
-            for k in range(abi.MAX_PATCHES + 1):
-                c.alter_patch[k] = int(bool(pt.alter_patch.get(k, False))) if k <= n else 0
-            c.x_centroid, c.y_centroid, c.z_centroid = pt.x_centroid, pt.y_centroid, pt.z_centroid
-            c.length_x, c.length_y, c.length_z = pt.length_x, pt.length_y, pt.length_z
-            c.radius, c.epsilon, c.smooth_coeff, c.pres = pt.radius, pt.epsilon, pt.smooth_coeff, pt.pres
-            for k in range(3):
-                c.radii[k], c.normal[k], c.vel[k] = pt.radii[k], pt.normal[k], pt.vel[k]
-            for k in range(abi.MAX_FLUIDS):
-                c.alpha_rho[k], c.alpha[k] = pt.alpha_rho[k], pt.alpha[k]
-        zs, ys, xs = lay.interior_slices()
-        sl = (xs, ys, zs)
-        keep, ptrs = [], (abi.c_double_p * 3)()
-        dmin = []
-        for d in range(nd):
-            cb = cb_glb[d]
-            cc = np.ascontiguousarray(((cb[1:] + cb[:-1]) / 2.0)[sl[d]])
-            dmin.append(float(np.min(cb[1:] - cb[:-1])))
-            keep.append(cc)
-            ptrs[d] = cc.ctypes.data_as(abi.c_double_p)
-        abi.check(self.L.mfc_b200_generate_initial_condition(n, arr, ptrs, min(dmin)))
+        arr = patch_array(self.cfg)
+        cc, ds_min = rank_cell_centres(self.cfg, self.layout, cb_glb)
+        ptrs = (abi.c_double_p * 3)()
+        for d, c in enumerate(cc):
+            ptrs[d] = c.ctypes.data_as(abi.c_double_p)
+        abi.check(self.L.mfc_b200_generate_initial_condition(len(arr), arr, ptrs, ds_min))
 
     def upload_ghosted(self, q_ghosted: np.ndarray) -> None:
         assert q_ghosted.shape == (self.E,) + self.ghost_shape and q_ghosted.dtype == np.float64

@@ -191,3 +191,41 @@ def test_p_main_loop_dt_tweak_and_last_iteration():
     t = sum(c[1] for c in pr.calls[:10])
     assert abs(t - 10 * cfg.dt) < 1e-18 and abs(pr.calls[10][1]) < 1e-15
     assert len(rows) == 11
+
+
+# ---- device-side initial condition: what the host hands to mfc_b200_generate_initial_condition ----
+def test_patch_array_mirrors_the_case_patches():
+    from microfc_b200 import abi
+    from microfc_b200.simulation import patch_array
+    cfg = cases.config(cases.shockbubble_3d(nc=32))
+    arr = patch_array(cfg)
+    assert len(arr) == cfg.num_patches == 3
+    for c, pt in zip(arr, cfg.patches):
+        assert c.geometry == pt.geometry and bool(c.smoothen) == pt.smoothen and c.smooth_patch_id == pt.smooth_patch_id
+        assert [bool(c.alter_patch[k]) for k in range(cfg.num_patches + 1)] == \
+               [bool(pt.alter_patch.get(k, False)) for k in range(cfg.num_patches + 1)]
+        assert all(c.alter_patch[k] == 0 for k in range(cfg.num_patches + 1, abi.MAX_PATCHES + 1))
+        assert (c.x_centroid, c.y_centroid, c.z_centroid, c.radius, c.pres) == \
+               (pt.x_centroid, pt.y_centroid, pt.z_centroid, pt.radius, pt.pres)
+        assert list(c.vel) == pt.vel and list(c.alpha_rho) == pt.alpha_rho and list(c.alpha) == pt.alpha
+    assert bool(arr[0].alter_patch[0]) and bool(arr[1].alter_patch[1]) and arr[2].smooth_patch_id == 1
+
+
+def test_rank_cell_centres_tile_the_global_grid():
+    from microfc_b200 import pre_process
+    from microfc_b200.domain import rank_layout
+    from microfc_b200.simulation import rank_cell_centres
+    cfg = cases.config(cases.shockbubble_3d(ncx=64, ncy=52, ncz=50))
+    cb = pre_process.generate_grid(cfg)
+    glb = [(c[1:] + c[:-1]) / 2.0 for c in cb]
+    got = [np.full_like(g, np.nan) for g in glb]
+    for r in range(8):
+        lay = rank_layout(r, 8, cfg)
+        cc, ds_min = rank_cell_centres(cfg, lay, cb)
+        zs, ys, xs = lay.interior_slices()
+        for d, sl in enumerate((xs, ys, zs)):
+            assert len(cc[d]) == lay.N[d] + 1
+            got[d][sl] = cc[d]
+        assert ds_min == min(float(np.min(c[1:] - c[:-1])) for c in cb)      # GLOBAL minimum on every rank
+    for d in range(3):
+        assert np.array_equal(got[d], glb[d])
