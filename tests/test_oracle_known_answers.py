@@ -14,6 +14,8 @@ derived independently of any implementation:
   7. 3-D extension: z-invariant data reproduces the 2-D run plane by plane (all three axes)
   8. emulated multi-rank run == single-rank run bitwise (m_mpi_proxy.fpp halo semantics)
   9. the -O3/OpenMP timing build (bench.py's cpu_baseline) agrees with the strict build
+ 10. viscous terms (both weno_Re_flux branches): a low-Mach sinusoidal shear wave decays like
+     exp(-nu k^2 t), nu = 1/(Re rho); the VCFL row of run_time.inf is dt/(Re dx^2)
 """
 import dataclasses
 
@@ -332,3 +334,43 @@ def test_timing_build_agrees_with_strict_build():
     assert oracle_lib.load("strict").orc_is_strict() == 1
     assert oracle_lib.load("timing").orc_is_strict() == 0
     assert (norm_linf(qt, qs, cfg) < 1e-10).all()
+
+
+# ---- 10. viscous shear-wave decay --------------------------------------------------------------
+@pytest.mark.parametrize("weno_Re_flux", [False, True])
+def test_viscous_shear_wave_decays_at_the_analytic_rate(weno_Re_flux):
+    """u(y, t) = U0 sin(2 pi y) exp(-nu (2 pi)^2 t) solves the viscous momentum equation for a
+    uniform low-Mach state (div u = 0, pressure uniform up to O(Mach^2) heating).  Pins
+    m_viscous.fpp / s_compute_viscous_source_flux in the oracle: tau_xy = (du/dy + dv/dx)/Re,
+    rhs(mom_x) += d tau_xy / dy, with 1/Re = sum alpha_i/Re_i."""
+    N, Nx, Re, U0, nsteps = 64, 32, 100.0, 0.01, 200
+    d = cases.viscous_2d(N=N - 1, Nt=nsteps, weno_Re_flux=weno_Re_flux)
+    d.update({'m': Nx - 1, 'n': N - 1, 'x_domain%beg': 0.0, 'x_domain%end': Nx / float(N), 'y_domain%beg': 0.0,
+              'y_domain%end': 1.0, 'bc_x%beg': -1, 'bc_x%end': -1, 'bc_y%beg': -1, 'bc_y%end': -1, 'run_time_info': 'T',
+              'fluid_pp(1)%gamma': 2.5, 'fluid_pp(2)%gamma': 2.5, 'fluid_pp(1)%pi_inf': 0.0, 'fluid_pp(2)%pi_inf': 0.0,
+              'dt': 0.2 * (1.0 / N) / np.sqrt(1.4)})
+    for i in (1, 2):
+        d[f'fluid_pp({i})%Re(1)'] = Re                             # shear viscosity only
+        d.pop(f'fluid_pp({i})%Re(2)', None)
+    cfg = dataclasses.replace(cases.config(d), t_step_stop=nsteps)
+    cb = pre_process.generate_grid(cfg)
+    y = (cb[1][1:] + cb[1][:-1]) / 2
+    q = np.zeros((cfg.sys_size, 1, N, Nx))
+    u = U0 * np.sin(2 * np.pi * y)[None, :, None] * np.ones((1, N, Nx))
+    q[0], q[1] = 0.5, 0.5                                          # rho = 1, two identical fluids
+    q[2], q[3] = u, 0.0
+    q[4] = 2.5 * 1.0 + 0.5 * u * u                                 # p = 1, gamma = 1.4
+    q[5], q[6] = 0.5, 0.5
+    o = oracle_lib.Oracle(cfg, cb)
+    o.set_q(q)
+    rows = oracle_lib.run_p_main(o, cfg)
+    out = o.get_q()
+    uu = out[2] / (out[0] + out[1])
+    amp = 2 * np.mean(uu[0, :, 0] * np.sin(2 * np.pi * y))
+    exact = np.exp(-(1.0 / Re) * (2 * np.pi) ** 2 * nsteps * cfg.dt)
+    assert abs(amp / U0 - exact) < (1e-5 if weno_Re_flux else 5e-4) * exact, (amp / U0, exact)
+    assert np.abs(uu - uu[:, :, :1]).max() == 0.0                  # x-invariant stays x-invariant, bitwise
+    assert np.abs(out[3]).max() < 1e-5 * U0 * 100                  # no spurious transverse momentum
+    # run_time.inf: VCFL = dt max(1/Re_1, 1/Re_2) / min(dx, dy)^2 (m_data_output.fpp:223-229)
+    dx = 1.0 / N
+    assert abs(rows[0][2][1] - cfg.dt / Re / dx ** 2) < 1e-12
