@@ -16,6 +16,8 @@ derived independently of any implementation:
   9. the -O3/OpenMP timing build (bench.py's cpu_baseline) agrees with the strict build
  10. viscous terms (both weno_Re_flux branches): a low-Mach sinusoidal shear wave decays like
      exp(-nu k^2 t), nu = 1/(Re rho); the VCFL row of run_time.inf is dt/(Re dx^2)
+ 11. order of accuracy: a smooth density wave advected with uniform u, p converges at fifth
+     order in the cell averages (WENO5 reconstruction + flux differencing + RK3 at small dt)
 """
 import dataclasses
 
@@ -374,3 +376,33 @@ def test_viscous_shear_wave_decays_at_the_analytic_rate(weno_Re_flux):
     # run_time.inf: VCFL = dt max(1/Re_1, 1/Re_2) / min(dx, dy)^2 (m_data_output.fpp:223-229)
     dx = 1.0 / N
     assert abs(rows[0][2][1] - cfg.dt / Re / dx ** 2) < 1e-12
+
+
+# ---- 11. order of accuracy ---------------------------------------------------------------------
+def test_smooth_advection_converges_at_fifth_order():
+    """rho(x, 0) = 1 + 0.2 sin(2 pi x), u = 1, p = 1, periodic: the exact solution is the
+    translated profile.  Cell AVERAGES are compared (the scheme is a finite-volume method:
+    m_rhs.fpp:567-576 differences face fluxes), so the error is the scheme's alone."""
+    errs = []
+    for N in (40, 80, 160):
+        d = cases.sod_1d(Nx=N - 1, Nt=10)
+        d.update({'bc_x%beg': -1, 'bc_x%end': -1, 'x_domain%beg': 0.0, 'x_domain%end': 1.0})
+        u0, T = 1.0, 0.25
+        dt = 0.2 * (1.0 / N) / (u0 + np.sqrt(1.4 / 0.8))
+        nsteps = int(round(T / dt))
+        d['dt'] = T / nsteps
+        cfg = dataclasses.replace(cases.config(d), t_step_stop=nsteps)
+        cb = pre_process.generate_grid(cfg)
+        xl, xr = cb[0][:-1], cb[0][1:]
+
+        def avg(a, b):
+            return 1.0 + 0.2 * (np.cos(2 * np.pi * a) - np.cos(2 * np.pi * b)) / (2 * np.pi * (b - a))
+        rho = avg(xl, xr)
+        q = np.zeros((cfg.sys_size, 1, 1, N))
+        q[0], q[1], q[2], q[3] = rho, rho * u0, 2.5 + 0.5 * rho * u0 * u0, 1.0
+        o = oracle_lib.Oracle(cfg, cb)
+        o.set_q(q)
+        oracle_lib.run_p_main(o, cfg)
+        errs.append(np.abs(o.get_q()[0, 0, 0] - avg(xl - u0 * T, xr - u0 * T)).mean())
+    orders = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert errs[0] < 5e-6 and all(o > 4.7 for o in orders), (errs, orders)
