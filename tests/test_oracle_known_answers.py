@@ -18,6 +18,8 @@ derived independently of any implementation:
      exp(-nu k^2 t), nu = 1/(Re rho); the VCFL row of run_time.inf is dt/(Re dx^2)
  11. order of accuracy: a smooth density wave advected with uniform u, p converges at fifth
      order in the cell averages (WENO5 reconstruction + flux differencing + RK3 at small dt)
+ 12. the symmetry boundary (bc = -2, m_rhs.fpp:704-720,822-835): the upper half of the symmetric
+     shock-bubble run on a half domain with a reflecting wall equals the full-domain run
 """
 import dataclasses
 
@@ -406,3 +408,22 @@ def test_smooth_advection_converges_at_fifth_order():
         errs.append(np.abs(o.get_q()[0, 0, 0] - avg(xl - u0 * T, xr - u0 * T)).mean())
     orders = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
     assert errs[0] < 5e-6 and all(o > 4.7 for o in orders), (errs, orders)
+
+
+# ---- 12. reflecting wall -----------------------------------------------------------------------
+def test_reflecting_wall_equals_the_mirrored_full_domain():
+    full = cases.shockbubble_2d_cells(180, 60, Nt=100)
+    cfgF = dataclasses.replace(cases.config(full), t_step_stop=60)
+    cbF = pre_process.generate_grid(cfgF)
+    q0F = pre_process.generate_initial_condition(cfgF, cbF)
+    qF, _ = oracle_run(cfgF, cbF, q0F)
+    half = dict(full)
+    half.update({'n': 29, 'y_domain%beg': 0.0, 'bc_y%beg': -2})   # y in [0, 0.5], wall at y = 0
+    cfgH = dataclasses.replace(cases.config(half), t_step_stop=60, dt=cfgF.dt)
+    cbH = pre_process.generate_grid(cfgH)
+    q0H = pre_process.generate_initial_condition(cfgH, cbH)
+    assert np.array_equal(q0H, q0F[:, :, 30:, :])
+    qH, _ = oracle_run(cfgH, cbH, q0H)
+    err = norm_linf(qH, qF[:, :, 30:, :], cfgH)
+    assert (err < 1e-11).all(), err
+    assert np.abs(qH - q0H).max() > 0
