@@ -20,6 +20,8 @@ derived independently of any implementation:
      order in the cell averages (WENO5 reconstruction + flux differencing + RK3 at small dt)
  12. the symmetry boundary (bc = -2, m_rhs.fpp:704-720,822-835): the upper half of the symmetric
      shock-bubble run on a half domain with a reflecting wall equals the full-domain run
+ 13. the alpha div(u) source (m_rhs.fpp:582-586): d(alpha)/dt = -div(alpha u) + alpha div(u) is
+     the advection equation, so a UNIFORM volume fraction stays uniform in a compressing flow
 """
 import dataclasses
 
@@ -427,3 +429,29 @@ def test_reflecting_wall_equals_the_mirrored_full_domain():
     err = norm_linf(qH, qF[:, :, 30:, :], cfgH)
     assert (err < 1e-11).all(), err
     assert np.abs(qH - q0H).max() > 0
+
+
+# ---- 13. volume-fraction source ----------------------------------------------------------------
+def test_uniform_volume_fraction_survives_compression():
+    """Water/air mixture with uniform alpha in a sinusoidal velocity field: the densities change
+    (div u != 0) but -div(alpha u) + alpha div(u) must cancel to round-off for uniform alpha."""
+    d = cases.kapila_1d(Nx=199, Nt=100)
+    d.update({'bc_x%beg': -1, 'bc_x%end': -1})
+    cfg = dataclasses.replace(cases.config(d), t_step_stop=80)
+    cb = pre_process.generate_grid(cfg)
+    x = (cb[0][1:] + cb[0][:-1]) / 2
+    N, a1 = cfg.m + 1, 0.3
+    ar1, ar2 = 1000.0 * a1, 50.0 * (1 - a1)
+    rho = ar1 + ar2
+    u = 20.0 * np.sin(2 * np.pi * (x - cfg.domain[0][0]) / (cfg.domain[0][1] - cfg.domain[0][0]))
+    G = a1 * cfg.gamma[0] + (1 - a1) * cfg.gamma[1]
+    Pi = a1 * cfg.pi_inf[0] + (1 - a1) * cfg.pi_inf[1]
+    q = np.zeros((cfg.sys_size, 1, 1, N))
+    q[0], q[1], q[2], q[3], q[4], q[5] = ar1, ar2, rho * u, G * 1e5 + Pi + 0.5 * rho * u * u, a1, 1 - a1
+    o = oracle_lib.Oracle(cfg, cb)
+    o.set_q(q)
+    oracle_lib.run_p_main(o, cfg)
+    out = o.get_q()
+    assert np.isfinite(out).all()
+    assert np.abs(out[4] - a1).max() < 1e-14 and np.abs(out[5] - (1 - a1)).max() < 1e-14
+    assert np.abs(out[0] + out[1] - rho).max() / rho > 1e-3       # the flow really compressed the mixture
