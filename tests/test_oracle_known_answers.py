@@ -17,7 +17,8 @@ derived independently of any implementation:
  10. viscous terms (both weno_Re_flux branches): a low-Mach sinusoidal shear wave decays like
      exp(-nu k^2 t), nu = 1/(Re rho); the VCFL row of run_time.inf is dt/(Re dx^2)
  11. order of accuracy: a smooth density wave advected with uniform u, p converges at fifth
-     order in the cell averages (WENO5 reconstruction + flux differencing + RK3 at small dt)
+     order in the cell averages (WENO5 reconstruction + flux differencing + RK3 at small dt);
+     second order for WENO3-JS + RK2, first order for WENO1 + RK1
  12. the symmetry boundary (bc = -2, m_rhs.fpp:704-720,822-835): the upper half of the symmetric
      shock-bubble run on a half domain with a reflecting wall equals the full-domain run
  13. the alpha div(u) source (m_rhs.fpp:582-586): d(alpha)/dt = -div(alpha u) + alpha div(u) is
@@ -383,14 +384,20 @@ def test_viscous_shear_wave_decays_at_the_analytic_rate(weno_Re_flux):
 
 
 # ---- 11. order of accuracy ---------------------------------------------------------------------
-def test_smooth_advection_converges_at_fifth_order():
+@pytest.mark.parametrize("weno_order,time_stepper,err40,order", [
+    (5, 3, 5e-6, 4.7),      # WENO5-JS: fifth order
+    (3, 2, 5e-3, 1.9),      # WENO3-JS with eps = 1e-16 falls to second order at the smooth extrema (known)
+    (1, 1, 3e-2, 0.9),      # piecewise constant + Euler: first order
+])
+def test_smooth_advection_converges_at_the_design_order(weno_order, time_stepper, err40, order):
     """rho(x, 0) = 1 + 0.2 sin(2 pi x), u = 1, p = 1, periodic: the exact solution is the
     translated profile.  Cell AVERAGES are compared (the scheme is a finite-volume method:
     m_rhs.fpp:567-576 differences face fluxes), so the error is the scheme's alone."""
     errs = []
     for N in (40, 80, 160):
         d = cases.sod_1d(Nx=N - 1, Nt=10)
-        d.update({'bc_x%beg': -1, 'bc_x%end': -1, 'x_domain%beg': 0.0, 'x_domain%end': 1.0})
+        d.update({'bc_x%beg': -1, 'bc_x%end': -1, 'x_domain%beg': 0.0, 'x_domain%end': 1.0,
+                  'weno_order': weno_order, 'time_stepper': time_stepper})
         u0, T = 1.0, 0.25
         dt = 0.2 * (1.0 / N) / (u0 + np.sqrt(1.4 / 0.8))
         nsteps = int(round(T / dt))
@@ -409,7 +416,7 @@ def test_smooth_advection_converges_at_fifth_order():
         oracle_lib.run_p_main(o, cfg)
         errs.append(np.abs(o.get_q()[0, 0, 0] - avg(xl - u0 * T, xr - u0 * T)).mean())
     orders = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
-    assert errs[0] < 5e-6 and all(o > 4.7 for o in orders), (errs, orders)
+    assert errs[0] < err40 and all(o > order for o in orders), (errs, orders)
 
 
 # ---- 12. reflecting wall -----------------------------------------------------------------------
