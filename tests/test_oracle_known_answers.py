@@ -23,6 +23,8 @@ derived independently of any implementation:
      shock-bubble run on a half domain with a reflecting wall equals the full-domain run
  13. the alpha div(u) source (m_rhs.fpp:582-586): d(alpha)/dt = -div(alpha u) + alpha div(u) is
      the advection equation, so a UNIFORM volume fraction stays uniform in a compressing flow
+ 14. examples/1D_kapilashocktube (water | air, stiffened gas) against the exact two-material
+     Riemann solution: star pressure and velocity, contact and shock positions, density in L1
 """
 import dataclasses
 
@@ -462,3 +464,62 @@ def test_uniform_volume_fraction_survives_compression():
     assert np.isfinite(out).all()
     assert np.abs(out[4] - a1).max() < 1e-14 and np.abs(out[5] - (1 - a1)).max() < 1e-14
     assert np.abs(out[0] + out[1] - rho).max() / rho > 1e-3       # the flow really compressed the mixture
+
+
+# ---- 14. water / air shock tube ----------------------------------------------------------------
+def stiffened_riemann_exact(x, t, x0, gl, pil, rl, pl, gr, pir, rr, pr):
+    """Exact solution (density) of the Riemann problem between two stiffened gases at rest,
+    p_l > p_r: left rarefaction, contact, right shock (Toro ch. 4 with p -> p + pi_inf)."""
+    Pl, Pr = pl + pil, pr + pir
+    cl, cr = np.sqrt(gl * Pl / rl), np.sqrt(gr * Pr / rr)
+
+    def f(p, g, pik, rk, pk, ck):
+        P, Pk = p + pik, pk + pik
+        if p > pk:
+            return (p - pk) * np.sqrt(2 / ((g + 1) * rk) / (P + (g - 1) / (g + 1) * Pk))
+        return 2 * ck / (g - 1) * ((P / Pk) ** ((g - 1) / (2 * g)) - 1)
+
+    lo, hi = pr, pl
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if f(mid, gl, pil, rl, pl, cl) + f(mid, gr, pir, rr, pr, cr) > 0:
+            hi = mid
+        else:
+            lo = mid
+    ps = 0.5 * (lo + hi)
+    us = 0.5 * (f(ps, gr, pir, rr, pr, cr) - f(ps, gl, pil, rl, pl, cl))
+    rsl = rl * ((ps + pil) / Pl) ** (1 / gl)
+    csl = cl * ((ps + pil) / Pl) ** ((gl - 1) / (2 * gl))
+    Pq, k = (ps + pir) / Pr, (gr - 1) / (gr + 1)
+    rsr = rr * (Pq + k) / (k * Pq + 1)
+    S = cr * np.sqrt((gr + 1) / (2 * gr) * Pq + (gr - 1) / (2 * gr))
+    xi = (x - x0) / t
+    rho = np.where(xi < -cl, rl, 0.0)
+    fan = (xi >= -cl) & (xi < us - csl)
+    rho = np.where(fan, rl * (2 / (gl + 1) + (gl - 1) / ((gl + 1) * cl) * (-xi)) ** (2 / (gl - 1)), rho)
+    rho = np.where((xi >= us - csl) & (xi < us), rsl, rho)
+    rho = np.where((xi >= us) & (xi < S), rsr, rho)
+    rho = np.where(xi >= S, rr, rho)
+    return rho, ps, us, S, rsr
+
+
+def test_kapila_water_air_shock_tube_matches_exact_riemann_solution():
+    N = 400
+    cfg, cb, q0 = setup_case(cases.kapila_1d(Nx=N - 1, Nt=int(6025 * N / 1000)))
+    o = oracle_lib.Oracle(cfg, cb)
+    o.set_q(q0)
+    oracle_lib.run_p_main(o, cfg)
+    q, prim = o.get_q(), o.get_prim()
+    x = (cb[0][1:] + cb[0][:-1]) / 2
+    T, dx = cfg.t_step_stop * cfg.dt, 1.0 / N
+    rho_ex, ps, us, S, rsr = stiffened_riemann_exact(x, T, 0.7, 4.4, 6e8, 1000., 1e9, 1.4, 0., 50., 1e5)
+    rho = (q[0] + q[1])[0, 0]
+    assert np.abs(rho - rho_ex).mean() / np.abs(rho_ex).mean() < 1e-2
+    i_star = np.argmin(np.abs(x - (0.7 + 0.5 * us * T)))           # star region, water side
+    assert abs(prim[3][0, 0][i_star] / ps - 1) < 5e-3              # p* = 14.19 MPa
+    assert abs(prim[2][0, 0][i_star] / us - 1) < 1e-3              # u* = 482.6 m/s
+    i0 = int(0.72 * N)
+    i_shock = np.where(rho[i0:] > 0.5 * (rsr + 50.0))[0].max() + i0
+    assert abs(x[i_shock] - (0.7 + S * T)) < 3 * dx
+    i_contact = np.where(q[4][0, 0] > 0.5)[0].max()                # alpha_water = 1/2
+    assert abs(x[i_contact] - (0.7 + us * T)) < 2 * dx
