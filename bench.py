@@ -32,6 +32,12 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm (`--impl reference`, cpu_baseline)
+# is meant to use every host core, and the OpenMP runtime reads the variable when it is first
+# loaded -- so decide it here, before anything that links libgomp is imported
+if os.environ.get("TORCHELASTIC_RUN_ID") or os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("MFC_B200_CPU_THREADS", str(os.cpu_count() or 1))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

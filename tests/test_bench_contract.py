@@ -53,6 +53,15 @@ def test_reference_arm_only_rank_zero_prints_under_torchrun():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_reference_arm_uses_every_host_core_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that."""
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-sample-cells", "64"],
+             env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2", "TORCHELASTIC_RUN_ID": "x", "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads(r.stdout.strip())
+    assert j["cpu_baseline"]["cores"] == os.cpu_count() and j["n_gpus"] == 2
+
+
 @pytest.mark.parametrize("workload", ["advection_2d_1024", "shockbubble_2d_4096", "shockdroplet_2d_viscous_2048", "sod_1d_400"])
 def test_reference_arm_covers_every_baseline_workload(workload):
     # (the shipped patches need >= ~100 cells per direction to be resolved at all -- the oracle
