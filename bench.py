@@ -331,10 +331,10 @@ def main():
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     hbm_peak, hbm_src, fp64_peak, fp64_src = measured_peaks()
-    sweeps = {k: v for k, v in prof.items() if k in ("k_xrow", "k_march3<y>", "k_march3<z>") and v[1] > 0}
+    sweeps = {k: v for k, v in prof.items() if k in ("k_xstream", "k_march3<y>", "k_march3<z>") and v[1] > 0}
     dom = max(sweeps, key=lambda k: sweeps[k][0])
     dom_t = sweeps[dom][0] / sweeps[dom][1]                      # average launch duration (CUDA events)
-    last_dir = {1: "k_xrow", 2: "k_march3<y>", 3: "k_march3<z>"}[nd]
+    last_dir = {1: "k_xstream", 2: "k_march3<y>", 3: "k_march3<z>"}[nd]
     cells_gpu = ncell_total // args.gpus
     dom_flops = sweep_flops_per_cell(E, nd, dom == last_dir) * cells_gpu
     traffic, traffic_src = None, None

@@ -218,6 +218,14 @@ int mfc_b200_profile_enable(int on);
 int mfc_b200_profile_get(int kernel_class, double *seconds, int64_t *launches);
 const char *mfc_b200_kernel_name(int kernel_class);
 
+/* Test hook: rebuild the ghost cells of q_cons_ts(1) in place (a following mfc_b200_download
+   returns them).  mode 0: the production ghost fill (m_rhs.fpp:686-908 / the NCCL halo
+   exchange).  mode 1: every periodic direction is filled by the halo-exchange kernels
+   (pack -> device copy in place of ncclSend/ncclRecv to myself -> unpack,
+   m_mpi_proxy.fpp:490-601,733-969) instead of the periodic boundary kernel; the two must agree
+   bit for bit, which checks the x / y / z pack and unpack index maps on a single GPU. */
+int mfc_b200_debug_fill_ghosts(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.mfc_b200_profile_get.argtypes = [C.c_int, c_double_p, C.POINTER(C.c_int64)]
     L.mfc_b200_kernel_name.argtypes = [C.c_int]
     L.mfc_b200_kernel_name.restype = C.c_char_p
+    L.mfc_b200_debug_fill_ghosts.argtypes = [C.c_int]
     _lib = L
     return L
 
@@ -126,5 +127,5 @@ EXPORTED_SYMBOLS = [
     "mfc_b200_download", "mfc_b200_download_prim", "mfc_b200_finalize", "mfc_b200_last_error",
     "mfc_b200_get_weno_coefficients", "mfc_b200_kernel_launches", "mfc_b200_state_snapshot",
     "mfc_b200_state_restore", "mfc_b200_timer_start", "mfc_b200_timer_stop", "mfc_b200_profile_enable", "mfc_b200_profile_get", "mfc_b200_kernel_name",
-    "mfc_b200_generate_initial_condition",
+    "mfc_b200_generate_initial_condition", "mfc_b200_debug_fill_ghosts",
 ]

@@ -28,10 +28,12 @@ struct SweepArgs {
     int rk_mode;           // 0: store RHS; 1..4: fused update, see rk_apply()
     int seg;               // cells per thread along the sweep (march kernels)
     int rows;              // rows per block (x kernel)
-    // x kernel, split launch: CTA blockIdx.x works on x tile blockIdx.x (< xb_n0) or blockIdx.x +
-    // xb_skip; xsplit = 1: interior tiles only (no x ghost column read), 2: the remaining tiles,
-    // 0: everything in one launch
-    int xsplit, xb_n0, xb_skip;
+    // x kernel: warp work items = xs_ntx x tiles x row blocks of `rows` rows (xs_items per plane).
+    // Tiles are balanced over cells xs_lo .. xs_hi, or (xs_strip > 0) the two boundary strips
+    // [0, xs_strip-1] and [N-xs_strip+1, N].  xsplit (set by the API for multi-rank runs whose x
+    // halo is still in flight) = 1: the cells that read no x ghost column, 2: the two boundary
+    // strips, 0: everything in one launch
+    int xsplit, xs_ntx, xs_lo, xs_hi, xs_strip, xs_items;
     // fused stability criterion (x kernel of stage 1, inviscid fast build): ICFL max of the
     // cells this kernel finishes, m_data_output.fpp:215-233; nullptr = off
     unsigned long long *stab_out;

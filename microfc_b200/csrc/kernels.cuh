@@ -12,7 +12,7 @@
 //   m_mpi_proxy.fpp:490-499,592-601 (+y) pack / unpack       -> k_halo_pack / k_halo_unpack
 //   m_variables_conversion.fpp:313-375 cons -> prim          -> k_prim
 //   m_weno.fpp:470-535 + m_riemann_solvers.fpp:132-327 +
-//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_xrow (x: warp-shuffle pencil)
+//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_xstream (x: warp-shuffle stream)
 //                                                               k_march3 (y / z: marching pencils)
 //   m_data_output.fpp:197-258 stability criteria             -> k_stability
 #pragma once
@@ -250,31 +250,34 @@ __device__ __forceinline__ void hllc(const double *L, const double *R, const dou
     const double s_R = fmax(uR + c_R, uL + c_L);
     const double mL = rho_L*(s_L - uL), mR = rho_R*(s_R - uR);
     const double s_S = (pres_R - pres_L + mL*uL - mR*uR)*rcp_fast3(mL - mR);
-    const bool left = !signbit(s_S);                     // xi_M = 1 (:254)
-    const double rho = left ? rho_L : rho_R, u = left ? uL : uR, pres = left ? pres_L : pres_R;
-    const double s_K = left ? s_L : s_R;
-    const double s_MP = left ? fmin(0.0, s_L) : fmax(0.0, s_R);
-    const double E_K = fma(left ? gamma_L : gamma_R, pres, left ? pi_inf_L : pi_inf_R) + 5e-1*rho*(left ? v2L : v2R);
-    const double da = s_K - s_S, db = s_K - u;
-    const double rab = rcp_fast3(da*db);
-    const double xi = db*db*rab;                         // (s_K - u_K)/(s_K - s_S)
-    const double p_over = pres*da*rab;                   // p_K/(s_K - u_K)
-    const double w = fma(s_MP, xi - 1.0, u);             // u_K + s_MP (xi_K - 1)
+    // The upwind side is taken by a BRANCH, not by selects: the sign of s_S is uniform over large
+    // parts of the flow, so most warps run one side only; selecting ~15 doubles per face costs
+    // ~60 issue slots (SEL/FSEL/MOV) that the branch does not.
+    auto side = [&](const double *K, double rho, double u, double pres, double s_K, double s_MP,
+                    double gamma, double pi_inf, double v2) {
+        const double E_K = fma(gamma, pres, pi_inf) + 5e-1*rho*v2;
+        const double da = s_K - s_S, db = s_K - u;
+        const double rab = rcp_fast3(da*db);
+        const double xi = db*db*rab;                     // (s_K - u_K)/(s_K - s_S)
+        const double p_over = pres*da*rab;               // p_K/(s_K - u_K)
+        const double w = fma(s_MP, xi - 1.0, u);         // u_K + s_MP (xi_K - 1)
 #pragma unroll
-    for (int i = 0; i < NF; i++) {
-        F[i] = (left ? L[i] : R[i])*w;
-        F[ADV + i] = (left ? L[ADV + i] : R[ADV + i])*w;
-    }
+        for (int i = 0; i < NF; i++) {
+            F[i] = K[i]*w;
+            F[ADV + i] = K[ADV + i]*w;
+        }
 #pragma unroll
-    for (int i = 0; i < ND; i++) {
-        const double vi = left ? L[MOM + i] : R[MOM + i];
-        if (i == NRM) F[MOM + i] = fma(rho, fma(u, u, s_MP*fma(xi, s_S, -u)), pres);
-        else F[MOM + i] = rho*vi*w;
-    }
-    F[EN] = fma(u, E_K + pres, s_MP*(fma(xi, fma(s_S - u, fma(rho, s_S, p_over), E_K), -E_K)));
-    uf = w;
+        for (int i = 0; i < ND; i++) {
+            if (i == NRM) F[MOM + i] = fma(rho, fma(u, u, s_MP*fma(xi, s_S, -u)), pres);
+            else F[MOM + i] = rho*K[MOM + i]*w;
+        }
+        F[EN] = fma(u, E_K + pres, s_MP*(fma(xi, fma(s_S - u, fma(rho, s_S, p_over), E_K), -E_K)));
+        uf = w;
 #pragma unroll
-    for (int i = 0; i < ND; i++) vs[i] = i == NRM ? w : (left ? L[MOM + i] : R[MOM + i]);
+        for (int i = 0; i < ND; i++) vs[i] = i == NRM ? w : K[MOM + i];
+    };
+    if (!signbit(s_S)) side(L, rho_L, uL, pres_L, s_L, fmin(0.0, s_L), gamma_L, pi_inf_L, v2L);   // xi_M = 1 (:254)
+    else side(R, rho_R, uR, pres_R, s_R, fmax(0.0, s_R), gamma_R, pi_inf_R, v2R);
 #else
     double vel_L_rms = 0.0, vel_R_rms = 0.0;                            // :138-145
 #pragma unroll
@@ -451,13 +454,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #define MFC_CTAS_Z 3
 #endif
 #ifndef MFC_RING_X
-#define MFC_RING_X 4
+#define MFC_RING_X 3
 #define MFC_WARPS_X 4
-#define MFC_CTAS_X 5
+#define MFC_CTAS_X 4
 #endif
 constexpr int kRingY = MFC_RING_Y;   // row slots of the y/z march ring: 5 live rows + the rows in flight
-constexpr int kRingX = MFC_RING_X;   // row slots of the x kernel: 1 live row + the rows in flight
-constexpr int kWarpCells = 30; // cells finished per warp and row in the x kernel
+constexpr int kRingX = MFC_RING_X;   // box slots of the x kernel: up to 2 per chunk + the boxes in flight
 // doubles per ring slot: E rows of W doubles, padded so that every slot starts on a 128-byte line
 // (the TMA destination alignment)
 __host__ __device__ constexpr int slot_doubles(int E, int W) { return (E*W + 15)/16*16; }
@@ -681,97 +683,218 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
 }
 
 // ------------------------------------------------------------------------------------------
-// x sweep.  Every WARP is an independent pipeline: it owns 30 consecutive cells of a row
-// and streams `rows` consecutive rows through its private 4-slot ring (one tensor-map bulk
-// copy of 40 columns x E variables per row, issued by lane 0 three rows ahead of the compute;
-// mbarrier per slot).  No block-wide barrier exists, so warps never wait for each other.
-// Within a row: lane = cell; every lane reconstructs its own cell (all E variables), the right
-// neighbour's left-face state arrives by warp shuffle, the lane solves the Riemann problem at
-// its right face, the left face's flux arrives by shuffle, and lanes 1..30 finish their cell.
+// x sweep.  Every WARP is an independent pipeline over a STREAM of cells: its work item is an x
+// tile [ja, jb] of `nr` consecutive rows, laid end to end as rows of Ls = max(jb-ja+7, 32)
+// stream entries (cells ja-3 .. jb+3 of a row, then the next row).  The warp walks the stream in
+// chunks of 32 entries, lane = entry, so that all 32 lanes do useful work whatever the row length
+// (a 512-cell row is 518 entries; the first kernel of this file's history finished 30 cells per
+// 32 lanes and needed 576 lane slots for it).  The stages of the scheme follow each other through
+// small per-warp rings in shared memory, each stage working on the entry its inputs are ready for:
+//   entry g     cons -> prim of the lane's own cell, raw values from the TMA box, result into the
+//               primitive ring (40 entries per variable)
+//   entry g-2   WENO reconstruction from ring entries g-4 .. g; the right-face state goes into an
+//               exchange ring (33 entries: the slot the 32 lanes leave untouched in a chunk is
+//               lane 31's value of the previous chunk, which lane 0 reads), the lane reads the
+//               state of entry g-3 and solves the Riemann problem at the face between g-3 and g-2
+//   entry g-3   the flux crosses lanes through a second exchange ring the same way; the lane
+//               finishes cell g-3 (flux difference, source term, 1-D: the TVD-RK statement)
+// Every shared-memory hand-over is one STS + one LDS per value (a 64-bit warp shuffle is two
+// instructions plus a select for the chunk boundary), the conversion runs once per cell, and the
+// boxes of consecutive chunks do not overlap.  This matters because the sweeps are ISSUE bound:
+// an FP64 warp instruction holds its scheduler's issue port for two cycles, so a kernel's time
+// is (2 x FP64 + other instructions) per scheduler -- see DESIGN.md 4.
+// A chunk lies in one row or, when it wraps, in two: each part is one tensor-map bulk copy of
+// 34 columns x E variables into a ring slot (box start rounded down to an even column, the TMA
+// unit wants 16-byte aligned starts; the part of a box before a row's first ghost column is
+// zero-filled and read by no lane that stores), and a lane picks the slot of its own row.
+// No block-wide barrier exists, so warps never wait for each other.
 // BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).  VISC: viscous run,
 // vel_src and Re_avg of every face are stored for k_visc.
 // ------------------------------------------------------------------------------------------
+constexpr int kPrimRing = 40;                      // entries of the primitive ring (>= 32 + 4, multiple of 8)
+constexpr int kXchRing = 33;                       // entries of the exchange rings (32 lanes + the carried one)
+__host__ __device__ constexpr int xstream_warp_doubles(int E) {   // per-warp shared memory besides the TMA ring
+    return E*kPrimRing + E*kXchRing + (E + 1)*kXchRing;
+}
+__host__ __device__ constexpr size_t xstream_smem(int E) {
+    return (size_t)kWarpsX*((kRingX*slot_doubles(E, kWX) + xstream_warp_doubles(E))*sizeof(double) + kRingX*sizeof(unsigned long long));
+}
+// cons -> prim of one cell in registers (m_variables_conversion.fpp:187-227, :353-362, :98-106);
+// the same statements as prim_in_place
+template <int NF, int ND>
+__device__ __forceinline__ void prim_regs(double (&q)[2*NF + ND + 1], const double *gam, const double *pinf) {
+    constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
+#if MFC_STRICT
+    double rho = 0.0, gamma = 0.0, pi_inf = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        rho = rho + q[i];
+        gamma = gamma + q[ADV + i]*gam[i];
+        pi_inf = pi_inf + q[ADV + i]*pinf[i];
+    }
+    rho = fmax(rho, 1e-16);
+    double dyn = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        const double mom = q[MOM + i];
+        const double u = mom/rho;
+        q[MOM + i] = u;
+        dyn = dyn + 5e-1*mom*u;
+    }
+    q[EN] = (q[EN] - dyn - pi_inf)/gamma;
+#else
+    double rho = q[0], gamma = q[ADV]*gam[0], pi_inf = q[ADV]*pinf[0];
+#pragma unroll
+    for (int i = 1; i < NF; i++) {
+        rho = rho + q[i];
+        gamma = fma(q[ADV + i], gam[i], gamma);
+        pi_inf = fma(q[ADV + i], pinf[i], pi_inf);
+    }
+    rho = fmax(rho, 1e-16);
+    double dyn = 0.0;
+    const double ir = rcp_fast3(rho), ig = rcp_fast3(gamma);
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+        const double mom = q[MOM + i];
+        const double u = mom*ir;
+        q[MOM + i] = u;
+        dyn = fma(5e-1*mom, u, dyn);
+    }
+    q[EN] = (q[EN] - dyn - pi_inf)*ig;
+#endif
+}
+
 template <int NF, int ND, int COEF, bool BC4, bool VISC, int WO>
-__global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = slot_doubles(E, kWX);
+    constexpr int PR = kPrimRing, XR = kXchRing;
     constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
+    static_assert(R >= 3, "a chunk needs up to two boxes, plus at least one in flight");
+    static_assert(kWX >= 34 && kWX % 2 == 0, "32 columns + one for the even-start rounding");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ring = reinterpret_cast<double *>(smem_raw) + warp*(R*SLOT);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsX*R*SLOT) + warp*R;
-    // x tile of this CTA.  A multi-rank run launches the x sweep in two parts (xsplit): the tiles
-    // that read no x ghost column first, while the x halo is still in flight, then the rest.
-    const int bx = (int)blockIdx.x < a.xb_n0 ? (int)blockIdx.x : (int)blockIdx.x + a.xb_skip;
-    const int jw = (bx*kWarpsX + warp)*kWarpCells;           // first cell finished by this warp
-    if (jw > g.N[0]) return;                           // whole warp out of range (no block barriers below)
-    const int k0 = blockIdx.y*a.rows, l = blockIdx.z;
-    const int nrows = min(a.rows, g.N[1] + 1 - k0);
-    const int x0 = jw - 4;                             // first staged column
+    double *prim = reinterpret_cast<double *>(smem_raw) + kWarpsX*R*SLOT + warp*xstream_warp_doubles(E);
+    double *xv = prim + E*PR, *xf = xv + E*XR;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(smem_raw) + kWarpsX*(R*SLOT + xstream_warp_doubles(E))) + warp*R;
+    // work item of this warp: x tile tix of row block rb in plane blockIdx.z
+    const int wi = (int)blockIdx.x*kWarpsX + warp;
+    if (wi >= a.xs_items) return;                      // no block barriers below
+    const int tix = wi % a.xs_ntx, rb = wi/a.xs_ntx;
+    int ja, jb;
+    if (a.xs_strip > 0) {                              // the two boundary strips of a split launch
+        ja = tix == 0 ? 0 : g.N[0] - a.xs_strip + 1;
+        jb = tix == 0 ? a.xs_strip - 1 : g.N[0];
+    } else {                                           // balanced tiles over cells xs_lo .. xs_hi
+        const long long W = a.xs_hi - a.xs_lo + 1;
+        ja = a.xs_lo + (int)(tix*W/a.xs_ntx);
+        jb = a.xs_lo + (int)((tix + 1)*W/a.xs_ntx) - 1;
+    }
+    const int k0 = rb*a.rows, l = blockIdx.z;
+    const int nr = min(a.rows, g.N[1] + 1 - k0);
+    const int Lt = jb - ja + 7;                        // entries of a row that exist: cells ja-3 .. jb+3
+    const int Ls = max(Lt, 32);                        // a chunk touches at most two rows
+    const int nload = (nr*Ls + 31) >> 5;               // chunks that bring new cells
+    const int nch = (nr*Ls + 3 + 31) >> 5;             // + the pipeline drain (the finish lags 3 entries)
     if (lane == 0) {
         for (int i = 0; i < R; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
-    // columns beyond the padded row are zero-filled by the TMA unit and count towards the bytes
-    auto issue = [&](int r, int slot) {
-        mbar_expect_tx(&bar[slot], (unsigned)(E*kWX*sizeof(double)));
-        tma_load_row(ring + slot*SLOT, &a.tm_q, x0 + kXoff, k0 + r + g.yoff, l + g.zoff, &bar[slot]);
+    // issue cursor: the next box to request belongs to the chunk whose lane 0 sits at entry ii of
+    // row ir; ipart = 1: its second part (the chunk wraps into row ir+1)
+    int ir = 0, ii = 0, ipart = 0, ichunk = 0, islot = 0, inflight = 0;
+    const int jbase = ja - 3 + kXoff;                  // tensor column of a row's entry 0
+    auto issue_one = [&]() {
+        const bool wrap = ii + 31 >= Ls && ir + 1 < nr;
+        if (lane == 0) {
+            mbar_expect_tx(&bar[islot], (unsigned)(E*kWX*sizeof(double)));
+            tma_load_row(ring + islot*SLOT, &a.tm_q, (jbase + ii - (ipart ? Ls : 0)) & ~1, k0 + ir + ipart + g.yoff, l + g.zoff, &bar[islot]);
+        }
+        if (++islot == R) islot = 0;
+        inflight++;
+        if (!ipart && wrap) ipart = 1;
+        else {
+            ipart = 0; ichunk++;
+            ii += 32;
+            if (ii >= Ls) { ii -= Ls; ir++; }
+        }
     };
-    if (lane == 0)
-        for (int r = 0; r < min(R, nrows); r++) issue(r, r);
+    while (inflight < R && ichunk < nload) issue_one();
 
-    const int j_raw = jw - 1 + lane;
-    const int j = min(j_raw, g.N[0] + 1);              // clamped lanes never store
-    const int sx = j - x0;                             // staged index of my cell (3 .. 34)
-    Weno<COEF, WO> weno;
-    weno.load(a, j);
-    const double rds = a.rds[j + g.b];
-    const unsigned full = 0xffffffffu;
-    const bool store_on = lane >= 1 && lane <= kWarpCells && j_raw <= g.N[0];
     const bool stab_on = a.stab_out != nullptr;
     double icfl = 0.0;
-    unsigned off = (unsigned)g.at(min(j, g.N[0]), k0, l);
     const unsigned usy = (unsigned)g.sy;
-
-    // Conversion runs ONE ROW AHEAD of the reconstruction, so that its dependent chain (LDS ->
-    // reciprocals -> STS) overlaps the register-only Riemann solve of the current row instead of
-    // standing in front of the reconstruction.  The warp stages 40 columns: a pass of 32 lanes
-    // per row (placed next to hllc below) plus a pass for columns 32..39 that would keep only 8
-    // lanes busy -- it serves two rows at once, every other row, with 16 lanes.
-    static_assert(kWX - 32 == 8 && R >= 3, "the pass over columns 32..39 serves two rows with 16 lanes");
-    mbar_wait(&bar[0], 0);                             // rows 0 and 1: arrival, row 0 fully converted
-    if (nrows > 1) mbar_wait(&bar[1], 0);
-    prim_in_place<NF, ND, kWX>(ring + lane, a.gammas, a.pi_infs);
-    if (lane < 16 && (lane < 8 || nrows > 1))
-        prim_in_place<NF, ND, kWX>((lane < 8 ? ring : ring + SLOT) + 32 + (lane & 7), a.gammas, a.pi_infs);
-    __syncwarp();
-    int slot = 0;
-    for (int r = 0; r < nrows; r++, off += usy) {
-        double *row = ring + slot*SLOT;
-        const int ka = r + 1, sa = ka % R;             // the row converted in this iteration
-        double *rowa = ring + sa*SLOT;
-        if ((ka & 1) == 0 && ka < nrows) {             // pair (ka, ka+1): arrival + the pass over columns 32..39
-            const int kb = ka + 1, sb = kb % R;
-            mbar_wait(&bar[sa], (unsigned)(ka/R) & 1u);
-            if (kb < nrows) mbar_wait(&bar[sb], (unsigned)(kb/R) & 1u);
-            if (lane < 16 && (lane < 8 || kb < nrows))
-                prim_in_place<NF, ND, kWX>((lane < 8 ? rowa : ring + sb*SLOT) + 32 + (lane & 7), a.gammas, a.pi_infs);
+    const unsigned off_row0 = (unsigned)g.at(0, k0, l);
+    int r0 = 0, i0 = 0, cslot = 0;                     // consume cursor: lane 0's row / entry, first slot
+    unsigned cphase = 0;
+    int il = lane, row = 0;                            // my entry g: position in its row, row
+    int ppos = lane;                                   // its slot in the primitive ring
+    int wpos = lane;                                   // my slot in the exchange rings
+#pragma unroll 1
+    for (int c = 0; c < nch; c++) {
+        // ---- entry g: conversion ------------------------------------------------------------
+        if (c < nload) {
+            const bool wrap = i0 + 31 >= Ls && r0 + 1 < nr;
+            int slotB = cslot + 1;
+            unsigned phaseB = cphase;
+            if (slotB == R) { slotB = 0; phaseB ^= 1u; }
+            mbar_wait(&bar[cslot], cphase);
+            if (wrap) mbar_wait(&bar[slotB], phaseB);
+            const int cA = jbase + i0;
+            const bool inB = wrap && i0 + lane >= Ls;
+            const double *src = (inB ? ring + slotB*SLOT + ((cA - Ls) & 1) : ring + cslot*SLOT + (cA & 1)) + lane;
+            double q[E];
+#pragma unroll
+            for (int v = 0; v < E; v++) q[v] = src[v*kWX];
+            prim_regs<NF, ND>(q, a.gammas, a.pi_infs);
+#pragma unroll
+            for (int v = 0; v < E; v++) prim[v*PR + ppos] = q[v];
+            fence_proxy_async();
+            __syncwarp();                              // ring entries visible; the warp is done with the boxes
+            const int nb = wrap ? 2 : 1;
+            inflight -= nb;
+            cslot += nb;
+            if (cslot >= R) { cslot -= R; cphase ^= 1u; }
+            i0 += 32;
+            if (i0 >= Ls) { i0 -= Ls; r0++; }
+            while (inflight < R && ichunk < nload) issue_one();
+        } else {
+            __syncwarp();
         }
+        // ---- entry g-2: reconstruction, Riemann problem at its left face -------------------------
+        int il2 = il - 2, row2 = row;
+        if (il2 < 0) { il2 += Ls; row2--; }
+        int il3 = il - 3, row3 = row;
+        if (il3 < 0) { il3 += Ls; row3--; }
+        const int j2 = ja - 3 + il2, j3 = ja - 3 + il3;
+        const bool row3_ok = row3 >= 0 && row3 < nr;
+        const bool store_on = row3_ok && il3 >= 3 && il3 <= Lt - 4;      // cells ja .. jb
+        const int jf = min(max(j3, -1), g.N[0]);       // clamped lanes never store
+        const unsigned off = off_row0 + (unsigned)min(max(row3, 0), nr - 1)*usy + (unsigned)jf;   // two's complement for jf = -1
+        int tp[5];                                     // ring slots of entries g-4 .. g
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            tp[t] = ppos - 4 + t;
+            if (tp[t] < 0) tp[t] += PR;
+        }
+        Weno<COEF, WO> weno;
+        weno.load(a, min(max(j2, -1), g.N[0] + 1));
+        const double rds = a.rds[max(jf, 0) + g.b];
         CellIn<E, ACC, RK> in;
         if (RK) load_cell<NF, ND, ACC, RK>(a, off, in);
-        const double *p = row + sx;
         double vL[E], vR[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
             double s[5];
 #pragma unroll
-            for (int t = 0; t < 5; t++) s[t] = p[v*kWX + (t - 2)];
+            for (int t = 0; t < 5; t++) s[t] = prim[v*PR + tp[t]];
             weno(s, vL[v], vR[v]);
         }
-        double pc[E];                                  // my cell's ring entry, kept for the finish
+        double pc[E];                                  // primitive variables of the cell I finish (entry g-3)
 #pragma unroll
-        for (int v = 0; v < E; v++) pc[v] = (RK || v >= ADV || stab_on) ? p[v*kWX] : 0.0;
+        for (int v = 0; v < E; v++) pc[v] = (RK || v >= ADV || stab_on) ? prim[v*PR + tp[1]] : 0.0;
 #if !MFC_STRICT
         if (stab_on) {                                 // ICFL, m_data_output.fpp:215-233 (inviscid)
             double rho = pc[0], gamma = pc[ADV]*a.gammas[0], pi_inf = pc[ADV]*a.pi_infs[0];
@@ -784,47 +907,55 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xrow(const __grid_consta
             const double cs = sqrt_ratio_fast(fma(gamma + 1.0, pc[NF + ND], pi_inf), gamma*rho);
             // dt/min_d(ds_d/(|u_d| + c)) = dt max_d((|u_d| + c)/ds_d)
             double m = (fabs(pc[NF]) + cs)*rds;
-            if (ND >= 2) m = fmax(m, (fabs(pc[NF + (ND >= 2 ? 1 : 0)]) + cs)*__ldg(a.rds_t[0] + k0 + r + g.b));
+            if (ND >= 2) m = fmax(m, (fabs(pc[NF + (ND >= 2 ? 1 : 0)]) + cs)*__ldg(a.rds_t[0] + k0 + min(max(row3, 0), nr - 1) + g.b));
             if (ND >= 3) m = fmax(m, (fabs(pc[NF + (ND >= 3 ? 2 : 0)]) + cs)*__ldg(a.rds_t[1] + l + g.b));
             if (store_on) icfl = fmax(icfl, a.dt*m);
         }
 #endif
-        fence_proxy_async();
-        __syncwarp();                                  // the warp is done with this slot
-        if (lane == 0 && r + R < nrows) issue(r + R, slot);
-        if (++slot == R) slot = 0;
-        double Rs[E];
+        const int rpos = wpos ? wpos - 1 : XR - 1;     // the slot of the entry below mine
 #pragma unroll
-        for (int v = 0; v < E; v++) Rs[v] = __shfl_down_sync(full, vL[v], 1);
+        for (int v = 0; v < E; v++) xv[v*XR + wpos] = vR[v];
+        __syncwarp();
+        double Lst[E];
+#pragma unroll
+        for (int v = 0; v < E; v++) Lst[v] = xv[v*XR + rpos];
         if (BC4) {
-            if (a.bc_beg == -4 && j_raw == -1) {       // m_riemann_solvers.fpp:480-487
+            if (a.bc_beg == -4 && j2 == 0) {           // m_riemann_solvers.fpp:480-487: qL(-1) = qR(0)
 #pragma unroll
-                for (int v = 0; v < E; v++) vR[v] = Rs[v];
+                for (int v = 0; v < E; v++) Lst[v] = vL[v];
             }
-            if (a.bc_end == -4 && j_raw == g.N[0]) {   // :515-523
+            if (a.bc_end == -4 && j2 == g.N[0] + 1) {  // :515-523: qR(m+1) = qL(m)
 #pragma unroll
-                for (int v = 0; v < E; v++) Rs[v] = vR[v];
+                for (int v = 0; v < E; v++) vL[v] = Lst[v];
             }
         }
         double F[E], uf;
         double vs[ND];
-        // columns 0..31 of the NEXT row (arrived: see the pair wait above / the prologue); past the
-        // last row this converts an idle slot, harmlessly
-        prim_in_place<NF, ND, kWX>(rowa + lane, a.gammas, a.pi_infs);
-        hllc<NF, ND, 0>(vR, Rs, a.gammas, a.pi_infs, F, uf, vs);
-        if (VISC && lane <= kWarpCells && j_raw <= g.N[0])   // faces -1/2 .. N+1/2, keyed by the left cell
-            store_visc_face<NF, ND>(a, off, vR, Rs, vs);
+        hllc<NF, ND, 0>(Lst, vL, a.gammas, a.pi_infs, F, uf, vs);
+        // faces ja-1/2 .. jb+1/2, keyed by the left cell (entry g-3; both entries lie in one row there)
+        if (VISC && row3_ok && il3 >= 2 && il3 <= Lt - 4)
+            store_visc_face<NF, ND>(a, off, Lst, vL, vs);
+        // ---- entry g-3: finish --------------------------------------------------------------------
+#pragma unroll
+        for (int v = 0; v < E; v++) xf[v*XR + wpos] = F[v];
+        xf[E*XR + wpos] = uf;
+        __syncwarp();
         double Fm[E], ufm;
 #pragma unroll
-        for (int v = 0; v < E; v++) Fm[v] = __shfl_up_sync(full, F[v], 1);
-        ufm = __shfl_up_sync(full, uf, 1);
+        for (int v = 0; v < E; v++) Fm[v] = xf[v*XR + rpos];
+        ufm = xf[E*XR + rpos];
         finish_cell2<NF, ND, 1, ACC, RK>(a, off, store_on, rds, pc, in, Fm, ufm, F, uf);
-        __syncwarp();                                  // the next row is converted for every lane
+        // my next entry: 32 further down the stream
+        il += 32;
+        if (il >= Ls) { il -= Ls; row++; }
+        ppos += 32;
+        if (ppos >= PR) ppos -= PR;
+        wpos = rpos;
     }
     if (stab_on) {                                     // all values >= 0: the bit pattern orders like the value
         unsigned long long b = (unsigned long long)__double_as_longlong(icfl);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(full, b, o));
+        for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
         if (lane == 0) atomicMax(a.stab_out, b);
     }
 }

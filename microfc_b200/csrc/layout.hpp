@@ -28,7 +28,7 @@ namespace mfc {
 constexpr int kXoff = 16;
 constexpr int kMaxFluids = 4;
 constexpr int kMaxE = 2*kMaxFluids + 3 + 1;
-constexpr int kWX = 40;        // doubles staged per warp, row and variable by the x kernel (36 used)
+constexpr int kWX = 34;        // columns per box and variable of the x kernel: 32 + the even-start rounding
 constexpr int kWY = 32;        // columns per warp in the y/z march
 constexpr int kNumWenoCoef = 27;   // 6 poly_L + 6 poly_R + 3 d_L + 3 d_R + 9 beta per cell
 

@@ -26,7 +26,7 @@ using namespace mfc;
 namespace {
 
 enum KernelClass { KC_BC = 0, KC_PRIM, KC_SWEEP_X, KC_SWEEP_Y, KC_SWEEP_Z, KC_STAB, KC_PACK, KC_UNPACK, KC_VISC, KC_PATCH, KC_COUNT };
-const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_xrow", "k_march3<y>", "k_march3<z>",
+const char *kKernelNames[KC_COUNT] = {"k_bc", "k_prim", "k_xstream", "k_march3<y>", "k_march3<z>",
                                       "k_stability", "k_halo_pack", "k_halo_unpack", "k_visc", "k_patches"};
 
 // NCCL is resolved at run time so the library loads (and every symbol is exported) on hosts
@@ -514,7 +514,8 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     // the checks of s_check_input_file that guard this path (m_start_up.fpp:147-229)
     const int nd = p->num_dims, nf = p->num_fluids;
     if (nd < 1 || nd > 3) return fail(MFC_B200_EINVAL, "Unsupported value of num_dims");
-    if (nf < 1 || nf > MFC_B200_MAX_FLUIDS) return fail(MFC_B200_EINVAL, "Unsupported value of num_fluids. Exiting ...");
+    if (nf < 1 || nf > MFC_B200_MAX_FLUIDS)
+        return fail(MFC_B200_EINVAL, "Unsupported value of num_fluids (kernels are instantiated for 1.." + std::to_string(MFC_B200_MAX_FLUIDS) + " fluids). Exiting ...");
     if (p->sys_size != 2*nf + nd + 1) return fail(MFC_B200_EINVAL, "sys_size /= 2*num_fluids + num_dims + 1");
     if (p->m <= 0) return fail(MFC_B200_EINVAL, "Unsupported value of m. Exiting ...");
     if (p->n < 0 || (nd > 1) != (p->n > 0)) return fail(MFC_B200_EINVAL, "Unsupported value of n. Exiting ...");
@@ -889,5 +890,49 @@ int mfc_b200_profile_get(int kc, double *seconds, int64_t *launches) {
 }
 
 const char *mfc_b200_kernel_name(int kc) { return kc >= 0 && kc < KC_COUNT ? kKernelNames[kc] : nullptr; }
+
+// Test hook: rebuild the ghost cells of q_cons_ts(1) in place.
+//   mode 0: the production path (fill_ghosts: k_bc for physical sides, pack / NCCL / unpack for
+//           processor boundaries)
+//   mode 1: every PERIODIC direction is filled by the halo-exchange kernels instead of k_bc --
+//           k_halo_pack of my first / last b layers, a device-to-device copy standing in for
+//           ncclSend/ncclRecv to myself, k_halo_unpack into the opposite ghost layers -- in the
+//           reference's direction order (m_rhs.fpp:692-905).  On one GPU this exercises the
+//           x, y and z pack / unpack index maps (m_mpi_proxy.fpp:490-601, 733-969) against the
+//           periodic ghost fill, which must agree bit for bit.
+int mfc_b200_debug_fill_ghosts(int mode) {
+    if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_debug_fill_ghosts before mfc_b200_upload");
+    double *q = S.state[S.cur];
+    int rc;
+    if (mode == 0) {
+        if ((rc = fill_ghosts(q))) return rc;
+    } else {
+        for (int d = 0; d < S.nd; d++) {
+            if (S.bc[d][0] == -1 && S.bc[d][1] == -1) {
+                const size_t n = (size_t)slab_count(S.g, d)*S.E;
+                double *buf = nullptr;
+                CK(cudaMalloc(&buf, 4*n*sizeof(double)));
+                for (int s = 0; s < 2; s++) {
+                    HaloArgs h{S.g, q, buf + s*n, d, s, S.E};
+                    Scope sc(KC_PACK); sc.done(S.L->halo_pack(h, S.st));
+                }
+                // my first layers are my end neighbour's (= my own) ... beg-side message and vice versa
+                CK(cudaMemcpyAsync(buf + 2*n, buf + n, n*sizeof(double), cudaMemcpyDeviceToDevice, S.st));   // last layers -> beg ghosts
+                CK(cudaMemcpyAsync(buf + 3*n, buf, n*sizeof(double), cudaMemcpyDeviceToDevice, S.st));       // first layers -> end ghosts
+                for (int s = 0; s < 2; s++) {
+                    HaloArgs h{S.g, q, buf + (2 + s)*n, d, s, S.E};
+                    Scope sc(KC_UNPACK); sc.done(S.L->halo_unpack(h, S.st));
+                }
+                CK(cudaStreamSynchronize(S.st));
+                CK(cudaFree(buf));
+            } else if ((rc = physical_bc_dir(q, d))) {
+                return rc;
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(S.st));
+    CK(cudaGetLastError());
+    return 0;
+}
 
 }  // extern "C"
