@@ -79,8 +79,14 @@ def step_flops_per_cell(E: int, nd: int) -> int:
     return 3 * per_rhs
 
 
-def workload_case(name: str, n_gpus: int, cells: int | None):
+def workload_case(name: str, n_gpus: int, cells: int | None, strong: bool = False):
+    """weak scaling: `cells` per GPU and direction, the global grid grows with the topology;
+    strong scaling: ONE global grid of `cells` per direction, split by the reference's rule
+    (m_mpi_proxy.fpp:163-203; 4096^2 on 8 ranks -> 4 x 2 blocks of 1024 x 2048)."""
     px, py, pz = TOPOLOGY[n_gpus] if name == "shockbubble_3d_512" else TOPOLOGY_2D[n_gpus]
+    topo = (px, py, pz)
+    if strong:
+        px = py = pz = 1
     if name == "shockbubble_3d_512":
         nc = cells or 512
         d = cases.shockbubble_3d(ncx=nc * px, ncy=nc * py, ncz=nc * pz, Nt=10 ** 6)
@@ -98,7 +104,6 @@ def workload_case(name: str, n_gpus: int, cells: int | None):
         nc = cells or 400
         d = cases.sod_1d(Nx=nc * n_gpus - 1, Nt=10 ** 6)
         d['dt'] = d['dt'] * 400.0 / nc
-        px, py, pz = n_gpus, 1, 1
         desc = f"examples/1D_sodshocktube, {nc} cells per GPU (BASELINE configs[0], the reference's own CPU-runnable case)"
     elif name == "shockdroplet_2d_viscous_2048":
         nc = cells or 2048
@@ -110,7 +115,11 @@ def workload_case(name: str, n_gpus: int, cells: int | None):
                 "(BASELINE configs[3]: 8192x4096 on 8 GPUs)")
     else:
         raise SystemExit(f"unknown workload {name}")
-    return cases.config(d), desc, (px, py, pz)
+    if strong:
+        desc = desc.replace("cells per GPU", "cells in total (one grid, strong-scaled)")
+    if name == "sod_1d_400":
+        topo = (n_gpus, 1, 1)
+    return cases.config(d), desc, topo
 
 
 class ClockSampler:
@@ -147,6 +156,21 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def fp64_peak_in_run(device_index: int):
+    """tools/fp64_peak (DFMA micro-benchmark, built by __graft_entry__.build()) on this rank's GPU,
+    right before the workload: the FP64 roof of THIS box at THIS moment (MEASURED_PEAKS.json has
+    no FP64 entry).  None if the binary is missing."""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device_index))
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     hbm, src = HBM_FALLBACK_GBS, "fallback"
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -164,6 +188,24 @@ def measured_peaks():
         except Exception:
             pass
     return hbm, src, fp64, fsrc
+
+
+def parity_note(workload: str):
+    """Where the parity of this workload's kernels is established (tests/, on the GPU) and what the
+    fast build's measured deviation from the oracle is: the north-star gate is 1e-10; the water/air
+    cases exceed it in the fast build (the strict build is bitwise equal to the oracle on all)."""
+    note = {"gate": 1e-10, "strict_build": "bitwise equal to the CPU oracle after 100 RK3 steps (tests/test_gpu_parity.py)",
+            "evidence": "profiles/r02_fast_build_linf.txt"}
+    rel = {"shockbubble_3d_512": ["shockbubble_3d"], "shockbubble_2d_4096": ["shockbubble_2d"], "advection_2d_1024": ["advection_2d"],
+           "sod_1d_400": ["sod_1d"], "shockdroplet_2d_viscous_2048": ["shockdroplet_2d_viscous", "shockdroplet_2d_inviscid"]}[workload]
+    fp = os.path.join(ROOT, "profiles", "r02_fast_build_linf.txt")
+    if os.path.exists(fp):
+        for line in open(fp):
+            w = line.split()
+            if len(w) >= 8 and w[0] == "FASTLINF" and w[1] in rel:
+                note.setdefault("fast_build", {})[w[1]] = {"linf": float(w[3]), "linf_per_variable": float(w[5]), "test_bound": float(w[7]),
+                                                           "oracle_1ulp_sensitivity": float(w[9]) if len(w) >= 10 else None}
+    return note
 
 
 def cpu_reference_run(cfg_full: CaseConfig, steps: int, warmup: int, sample_cells: int):
@@ -197,7 +239,7 @@ def cpu_reference_run(cfg_full: CaseConfig, steps: int, warmup: int, sample_cell
     ncell = int(np.prod(cfg.shape_glb))
     q = o.get_q()
     assert np.isfinite(q).all()
-    return {"value": ncell * steps / secs / 1e6, "unit": "Mcell-steps/s", "cores": oracle_lib.load("timing").orc_num_threads(),
+    return {"cells_run": ncell, "value": ncell * steps / secs / 1e6, "unit": "Mcell-steps/s", "cores": oracle_lib.load("timing").orc_num_threads(),
             "kind": "port", "sample": f"{sample}, {steps} steps after {warmup} warm-up, all host threads (OpenMP); "
             "the Fortran reference cannot be built in this image", "ms_per_step": secs / steps * 1e3,
             "grind_ns_per_cell_eq_rhs": secs / steps / (ncell * cfg.sys_size * 3) * 1e9}
@@ -212,6 +254,8 @@ def main():
     ap.add_argument("--workload", default="shockbubble_3d_512")
     ap.add_argument("--cells", type=int, default=None, help="cells per GPU and direction (default: the BASELINE size)")
     ap.add_argument("--cpu-sample-cells", type=int, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --cells per GPU (default); strong: one global grid of --cells per direction over all GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -223,22 +267,33 @@ def main():
     if args.gpus not in TOPOLOGY:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
     K, W = args.steps, max(args.warmup, 0)
-    cfg, desc, topo = workload_case(args.workload, args.gpus, args.cells)
+    strong = args.scaling == "strong"
+    cfg, desc, topo = workload_case(args.workload, args.gpus, args.cells, strong)
     nd, E = cfg.num_dims, cfg.sys_size
     ncell_total = int(np.prod(cfg.shape_glb))
+    if strong:
+        from microfc_b200.domain import processor_topology
+        topo = processor_topology(args.gpus, cfg)
+    state_mb = ncell_total // args.gpus * E * 8 / 1e6
     config = {"workload": desc, "cells_total": ncell_total, "cells_per_gpu": ncell_total // args.gpus,
               "sys_size": E, "num_dims": nd, "time_stepper": "SSP-RK3", "weno_order": 5, "riemann_solver": "HLLC",
               "run_time_info": bool(cfg.run_time_info), "decomposition": "x".join(map(str, topo)),
-              "l2": "state (>= 9 GB per GPU at the default size) is far larger than the 126 MB L2; no flush needed"}
+              "l2": (f"state of {state_mb:.0f} MB per GPU (x3 stage buffers + RHS) " +
+                     ("is far larger than the 126 MB L2; no flush needed" if state_mb * 4 > 4 * 126 else
+                      "is comparable to the 126 MB L2: a step touches 4 such buffers in turn, nothing is flushed explicitly"))}
 
     if args.impl == "reference":
         if rank != 0:
             return
         sample = args.cpu_sample_cells or {3: 128, 2: 1024, 1: 400}[nd]
         r = cpu_reference_run(cfg, K, W, sample)
+        # the CPU arm runs a bounded SAMPLE of the workload (same case, fewer cells): its config says
+        # what was actually run; throughput per cell is what carries over to the full size
+        config = dict(config, cells_total=r["cells_run"], cells_per_gpu=None, decomposition="1 CPU process, OpenMP",
+                      sample_of=f"{ncell_total} cells ({desc})", workload=f"{desc} -- CPU arm: {r['sample'].split(',')[0]}")
         line = {"impl": "reference", "metric": "Mcell-steps/s", "value": r["value"], "unit": "Mcell-steps/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "grind_ns_per_cell_eq_rhs": r["grind_ns_per_cell_eq_rhs"],
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -269,6 +324,7 @@ def main():
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
 
+    peak_run = fp64_peak_in_run(local_rank) if rank == 0 else None
     from microfc_b200.simulation import Simulation
     cb = pre_process.generate_grid(cfg)
     sim = Simulation(cfg, cb, rank=rank, num_procs=world, device=local_rank, broadcast_id=bcast_id if world > 1 else None)
@@ -291,7 +347,13 @@ def main():
         sim.step(t_step, dt); t_step += 1
     sampler = ClockSampler(local_rank)
     sampler.start()
-    sim.profile(True)
+    # per-kernel launch durations (the roofline's numerator) come from a CUDA-event pair around every
+    # launch on the launching stream, inside the timed region -- except on grids small enough for the
+    # library to replay a step as a CUDA graph (< 4 M cells, single rank): there the event records
+    # would both cost as much as the kernels and disable the graph, so they get their own pass below
+    prof_in_timed = world > 1 or ncell_total >= (4 << 20) or os.environ.get("MFC_B200_GRAPH") == "0"
+    if prof_in_timed:
+        sim.profile(True)
     launches0 = sim.kernel_launches()
     barrier(); sim.sync()
     sim.timer_start()
@@ -302,6 +364,11 @@ def main():
     barrier()
     secs = max_over_ranks(secs)
     launches = sim.kernel_launches() - launches0
+    if not prof_in_timed:
+        sim.profile(True)
+        for _ in range(min(K, 20)):
+            sim.step(t_step, dt); t_step += 1
+        sim.sync()
     prof = sim.profile_report()
     sim.profile(False)
     clocks = sampler.stop()
@@ -331,6 +398,13 @@ def main():
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     hbm_peak, hbm_src, fp64_peak, fp64_src = measured_peaks()
+    if peak_run and peak_run.get("fp64_dfma_tflops_sustained"):
+        fp64_peak = float(peak_run["fp64_dfma_tflops_sustained"])
+        fp64_src = "measured in this run, right before the workload (tools/fp64_peak: independent DFMA chains, all SMs)"
+    if world > 1:                                                 # every rank needs rank 0's figure
+        t = torch.tensor([fp64_peak], dtype=torch.float64, device="cuda")
+        dist.broadcast(t, src=0)
+        fp64_peak = float(t.item())
     sweeps = {k: v for k, v in prof.items() if k in ("k_xstream", "k_march3<y>", "k_march3<z>") and v[1] > 0}
     dom = max(sweeps, key=lambda k: sweeps[k][0])
     dom_t = sweeps[dom][0] / sweeps[dom][1]                      # average launch duration (CUDA events)
@@ -338,7 +412,9 @@ def main():
     cells_gpu = ncell_total // args.gpus
     dom_flops = sweep_flops_per_cell(E, nd, dom == last_dir) * cells_gpu
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_v4_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_v5_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_v4_traffic.json")
     if os.path.exists(tp) and nd == 3 and E == 8:
         # DRAM bytes per cell of this kernel from the committed ncu --set full capture (256^3, same
         # kernels): one stage-1 launch and two stage-2/3 launches per step
@@ -366,20 +442,24 @@ def main():
     kernel_share = {k: {"seconds": v[0], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
 
     cpu = None
-    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         sample = args.cpu_sample_cells or {3: 128, 2: 1024, 1: 400}[nd]
         r = cpu_reference_run(cfg, 3, 1, sample)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    barrier()
 
     if rank == 0:
         line = {"metric": "Mcell-steps/s", "value": value, "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": K,
-                "warmup": W, "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                "warmup": W, "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "grind_ns_per_cell_eq_rhs": secs / K / (ncell_total * E * 3) * 1e9,
                 "gflops_algorithmic": step_flops_per_cell(E, nd) * ncell_total * K / secs / 1e9,
                 "e2e": e2e, "gpu_launches": launches * world, "clocks": clocks,
-                "roofline": roof, "roofline_hbm": roof_hbm, "kernel_time": kernel_share, "cpu_baseline": cpu,
-                "icfl_last": icfl}
+                "roofline": roof, "roofline_hbm": roof_hbm, "kernel_time": kernel_share,
+                "kernel_time_source": "CUDA events around every launch, " + ("inside the timed region" if prof_in_timed else
+                                      "separate pass right after the timed region (the timed steps replay a CUDA graph)"),
+                "cpu_baseline": cpu,
+                "icfl_last": icfl, "fp64_peak_run": peak_run, "parity": parity_note(args.workload)}
         emit(line)
     sim.close()
     if dist is not None:

@@ -1,7 +1,7 @@
 """The reference's example cases, restated as flat MFC case dictionaries with the resolution
 as a parameter (BASELINE.json configs run them at other sizes than shipped).  At the shipped
 resolution each function reproduces the JSON its ``examples/<name>/case.py`` prints
-(checked by tests/test_cases.py when /root/reference is present).
+(checked by tests/test_host_logic.py when /root/reference is present).
 
 ``shockbubble_3d`` is an EXTENSION with no reference counterpart (the reference is 1-D/2-D).
 """
@@ -229,6 +229,44 @@ def viscous_2d(N: int = 50, Nt: int = 10, weno_Re_flux: bool = True) -> Dict:
         'fluid_pp(1)%Re(1)': 0.0001, 'fluid_pp(1)%Re(2)': 0.0001,
         'fluid_pp(2)%Re(1)': 0.0001, 'fluid_pp(2)%Re(2)': 0.0001,
     }
+
+
+def viscous_wave_2d(N: int = 48, Nx: int = 32, Nt: int = 100, weno_Re_flux: bool = True, bc_y: int = -1) -> Dict:
+    """A smooth two-fluid low-Mach state for the viscous terms (no reference example has one: in
+    examples/2D_viscous the velocity is piecewise constant, so the WENO-reconstructed
+    divergence-theorem gradients of m_viscous.fpp:200-217 vanish identically).  The patches only
+    lay down a uniform background; the parity tests overwrite the state with
+    :func:`viscous_wave_state`, whose velocity, density and volume fraction vary in x AND y so that
+    every stress component (shear and bulk, both fluids' Re) is active."""
+    d = viscous_2d(N=N - 1, Nt=Nt, weno_Re_flux=weno_Re_flux)
+    d.update({'m': Nx - 1, 'n': N - 1, 'x_domain%beg': 0.0, 'x_domain%end': Nx / float(N), 'y_domain%beg': 0.0,
+              'y_domain%end': 1.0, 'bc_x%beg': -1, 'bc_x%end': -1, 'bc_y%beg': bc_y, 'bc_y%end': bc_y,
+              'run_time_info': 'T', 'fluid_pp(1)%gamma': 2.5, 'fluid_pp(2)%gamma': 1.0 / (1.6 - 1.0),
+              'fluid_pp(1)%pi_inf': 0.0, 'fluid_pp(2)%pi_inf': 0.0, 'dt': 0.2 * (1.0 / N) / math.sqrt(1.4),
+              'fluid_pp(1)%Re(1)': 600.0, 'fluid_pp(1)%Re(2)': 360.0, 'fluid_pp(2)%Re(1)': 210.0, 'fluid_pp(2)%Re(2)': 480.0})
+    return d
+
+
+def viscous_wave_state(cfg: CaseConfig, cb):
+    """Conservative state (E, 1, Ny, Nx) of :func:`viscous_wave_2d`: p = 1, Mach ~ 0.05."""
+    import numpy as np
+    x = (cb[0][1:] + cb[0][:-1]) / 2
+    y = (cb[1][1:] + cb[1][:-1]) / 2
+    Lx = cb[0][-1] - cb[0][0]
+    X, Y = np.meshgrid(2 * np.pi * x / Lx, 2 * np.pi * y)          # (Ny, Nx)
+    U0 = 0.05
+    a1 = 0.5 + 0.2 * np.sin(Y) * np.cos(X)
+    r1, r2 = 1.0 + 0.1 * np.cos(Y), 0.6 + 0.05 * np.sin(X + Y)
+    u = U0 * (np.sin(Y) + 0.5 * np.cos(X))
+    v = 0.3 * U0 * np.sin(X + Y)
+    q = np.zeros((cfg.sys_size, 1) + X.shape)
+    q[0, 0], q[1, 0] = a1 * r1, (1.0 - a1) * r2
+    rho = q[0, 0] + q[1, 0]
+    q[2, 0], q[3, 0] = rho * u, rho * v
+    gamma = a1 * cfg.gamma[0] + (1.0 - a1) * cfg.gamma[1]
+    q[4, 0] = gamma * 1.0 + 0.5 * rho * (u * u + v * v)
+    q[5, 0], q[6, 0] = a1, 1.0 - a1
+    return q
 
 
 def shearlayer_2d(Nx: int = 319, Ny: int = 159, Nt: int = 100) -> Dict:

@@ -1159,9 +1159,9 @@ __global__ void __launch_bounds__(256) k_prim(const __grid_constant__ PrimArgs a
     constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
     const GridDesc &g = a.g;
     const int nx = g.N[0] + 1 + 2*g.b;
-    const int jj = blockIdx.x*blockDim.x + threadIdx.x;
+    const int jj = blockIdx.y*blockDim.x + threadIdx.x;
     if (jj >= nx) return;
-    const int row = blockIdx.y + g.ey*blockIdx.z;  // (k, l) incl. ghosts
+    const int row = blockIdx.x;                    // (k, l) incl. ghosts: k + ey*l (gridDim.x has no 65535 cap)
     const long long cell = (long long)(kXoff - g.b + jj) + (long long)g.pitch*row;
     const long long fs = g.fstride;
     double rho = 0.0, gamma = 0.0, pi_inf = 0.0;   // :187-227
@@ -1271,8 +1271,8 @@ template <int NF, int ND>
 __global__ void __launch_bounds__(256) k_stability(const __grid_constant__ StabArgs a) {
     constexpr int ADV = NF + ND + 1;
     const GridDesc &g = a.g;
-    const int j = blockIdx.x*blockDim.x + threadIdx.x;
-    const int k = blockIdx.y, l = blockIdx.z;
+    const int j = blockIdx.y*blockDim.x + threadIdx.x;
+    const int k = blockIdx.x % (g.N[1] + 1), l = blockIdx.x/(g.N[1] + 1);   // rows in gridDim.x: no 65535 cap
     double icfl = 0.0, vcfl = 0.0, Rc = 1.0e300;
     const bool visc = a.Re_size[0] > 0 || a.Re_size[1] > 0;
     if (j <= g.N[0]) {
@@ -1355,8 +1355,8 @@ __device__ __forceinline__ void weno_at(const double *f, long long cell, long lo
 template <int ND>
 __global__ void __launch_bounds__(128) k_visc_grad(const __grid_constant__ ViscArgs a) {
     const GridDesc &g = a.g;
-    const int j = (int)(blockIdx.x*blockDim.x + threadIdx.x) - 4;
-    const int k = ND > 1 ? (int)blockIdx.y - 4 : 0;
+    const int j = (int)(blockIdx.y*blockDim.x + threadIdx.x) - 4;
+    const int k = ND > 1 ? (int)blockIdx.x - 4 : 0;
     if (j > g.N[0] + 4) return;
     const int c[3] = {j, k, 0};
     const long long cell = g.at(j, k, 0), fs = g.fstride;
@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(128) k_visc_grad(const __grid_constant__ ViscA
 template <int NF, int ND>
 __global__ void __launch_bounds__(128, 4) k_visc(const __grid_constant__ ViscArgs a) {
     const GridDesc &g = a.g;
-    const int j = blockIdx.x*blockDim.x + threadIdx.x, k = blockIdx.y;
+    const int j = blockIdx.y*blockDim.x + threadIdx.x, k = blockIdx.x;
     if (j > g.N[0]) return;
     const int id = a.dir, b = g.b;
     const int c[3] = {j, k, 0};

@@ -104,6 +104,15 @@ struct Sim {
     double prof_s[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, sv0 = nullptr, sv1 = nullptr;
+    // one RK step captured as a CUDA graph (single rank): a step of a small grid is a dozen
+    // launches of a few microseconds each and is bound by launch latency, not by the kernels
+    struct StepGraph {
+        unsigned long long dt_bits; int stab, cur_before;          // key
+        cudaGraphExec_t exec;
+        int cur_after; const double *last_q_after; bool stab_pending_after; int64_t launches;
+    };
+    std::vector<StepGraph> graphs;
+    bool graph_on = false;
     std::string err;
 };
 Sim S;
@@ -171,6 +180,8 @@ void free_all() {
     if (S.st) { cudaStreamDestroy(S.st); S.st = nullptr; }
     for (auto &r : S.prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     S.prof_recs.clear();
+    for (auto &gr : S.graphs) cudaGraphExecDestroy(gr.exec);
+    S.graphs.clear();
     S.inited = S.uploaded = false;
 }
 
@@ -469,6 +480,49 @@ int do_step(int t_step, double dt, bool stab) {
     return 0;
 }
 
+// One RK step through a CUDA graph: captured on first use for this (dt, diagnostics, buffer
+// rotation) and replayed afterwards.  The host-side bookkeeping do_step performs (buffer rotation,
+// which state q_prim_vf reflects, a pending stability read-back) is recorded with the graph and
+// re-applied on replay.  Falls back to direct launches when capture is not possible.
+int do_step_graphed(int t_step, double dt, bool stab) {
+    unsigned long long bits;
+    std::memcpy(&bits, &dt, sizeof(bits));
+    for (auto &gr : S.graphs)
+        if (gr.dt_bits == bits && gr.stab == (int)stab && gr.cur_before == S.cur) {
+            CK(cudaGraphLaunch(gr.exec, S.st));
+            S.cur = gr.cur_after; S.last_q = gr.last_q_after; S.stab_pending = gr.stab_pending_after;
+            S.launches += gr.launches;
+            return 0;
+        }
+    if (S.graphs.size() >= 8) {                          // dt keeps changing: not worth caching
+        for (auto &gr : S.graphs) cudaGraphExecDestroy(gr.exec);
+        S.graphs.clear();
+    }
+    Sim::StepGraph gr{};
+    gr.dt_bits = bits; gr.stab = (int)stab; gr.cur_before = S.cur;
+    const int64_t l0 = S.launches;
+    if (cudaStreamBeginCapture(S.st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        return do_step(t_step, dt, stab);
+    }
+    const int rc = do_step(t_step, dt, stab);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(S.st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph) return fail(MFC_B200_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&gr.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(MFC_B200_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    gr.cur_after = S.cur; gr.last_q_after = S.last_q; gr.stab_pending_after = S.stab_pending;
+    gr.launches = S.launches - l0;
+    S.graphs.push_back(gr);
+    CK(cudaGraphLaunch(gr.exec, S.st));                  // the capture only recorded the work
+    return 0;
+}
+// graphs: single rank (no NCCL calls inside a capture), no per-kernel profiling events, and not the
+// final "convert only" call
+bool graph_ok(int t_step) { return S.graph_on && !S.comm && !S.prof && t_step != S.p.t_step_stop; }
+
 // host field (Fortran sf(-b:m+b, ...), x fastest, contiguous) <-> padded device plane.  The
 // host array crosses PCIe as ONE contiguous copy into a staging plane (the RHS accumulator, which
 // is scratch between steps) and is re-pitched by a kernel: a strided 2-D copy of 4 KB rows
@@ -642,6 +696,12 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
             }
     }
     CK(cudaStreamSynchronize(S.st));
+    {   // CUDA graphs per RK step: on by default for grids whose step is launch-bound (< 4 M cells);
+        // MFC_B200_GRAPH=0 / 1 forces it off / on
+        const char *e = std::getenv("MFC_B200_GRAPH");
+        const long long cells = (long long)(S.g.N[0] + 1)*(S.g.N[1] + 1)*(S.g.N[2] + 1);
+        S.graph_on = e ? e[0] != '0' : cells < (4LL << 20);
+    }
     S.cur = 0; S.launches = 0; S.inited = true; S.uploaded = false; S.last_q = nullptr;
     S.err.clear();
     return 0;
@@ -767,7 +827,7 @@ int mfc_b200_download_prim(double *const q_prim[]) {
 int mfc_b200_step(int t_step, double dt, double stab[3], double *step_seconds) {
     if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step before mfc_b200_upload");
     CK(cudaEventRecord(S.sv0, S.st));
-    int rc = do_step(t_step, dt, S.p.run_time_info != 0);
+    int rc = graph_ok(t_step) ? do_step_graphed(t_step, dt, S.p.run_time_info != 0) : do_step(t_step, dt, S.p.run_time_info != 0);
     if (rc) return rc;
     CK(cudaEventRecord(S.sv1, S.st));
     CK(cudaStreamSynchronize(S.st));
@@ -780,7 +840,7 @@ int mfc_b200_step(int t_step, double dt, double stab[3], double *step_seconds) {
 int mfc_b200_step_async(int t_step, double dt, int n_steps) {
     if (!S.uploaded) return fail(MFC_B200_ESTATE, "mfc_b200_step_async before mfc_b200_upload");
     for (int s = 0; s < n_steps; s++) {
-        int rc = do_step(t_step + s, dt, false);
+        int rc = graph_ok(t_step + s) ? do_step_graphed(t_step + s, dt, false) : do_step(t_step + s, dt, false);
         if (rc) return rc;
     }
     return 0;

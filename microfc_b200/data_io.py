@@ -89,7 +89,10 @@ def write_restart_parallel(case_dir: str, t_step: int, q_block: np.ndarray, cfg:
     assert q_block.shape[1:] == (zs.stop - zs.start, ys.stop - ys.start, xs.stop - xs.start)
     fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o644)
     try:
-        if os.fstat(fd).st_size < E * var_bytes:
+        # the reference deletes an existing file first (MPI_FILE_DELETE, m_data_output.fpp:506-509);
+        # every rank computes the same size, so setting it exactly is race-free and drops the
+        # trailing bytes of a stale, larger file
+        if os.fstat(fd).st_size != E * var_bytes:
             os.ftruncate(fd, E * var_bytes)
         for v in range(E):
             for iz, z in enumerate(range(zs.start, zs.stop)):

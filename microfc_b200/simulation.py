@@ -218,7 +218,10 @@ class Simulation:
             mytime = mytime + dt                                        # :214
             stab = self.step(t_step, dt)                                # :229-235
             rows.append((t_step, dt, stab))
-            if cfg.run_time_info and self.rank == 0:                    # m_data_output.fpp:296-305
+            # m_data_output.fpp:296-305: rank 0 detects it and calls s_mpi_abort, which takes every rank
+            # down.  The all-reduced criteria are identical on every rank, so each one raises by itself
+            # (a rank that carried on would hang in the next halo exchange).
+            if cfg.run_time_info:
                 if stab[0] != stab[0]:
                     raise FloatingPointError("ICFL is NaN. Exiting ...")
                 if stab[0] > 1.0:

@@ -11,13 +11,15 @@ from microfc_b200.case import CaseConfig
 import oracle_lib
 
 
-def setup_case(case_dict, n_steps=None):
-    """case dictionary -> (cfg, global cell boundaries, initial conservative state)."""
+def setup_case(case, n_steps=None):
+    """case dictionary, or (case dictionary, state function) for cases whose initial state is not
+    laid down by patches -> (cfg, global cell boundaries, initial conservative state)."""
+    case_dict, state = case if isinstance(case, tuple) else (case, None)
     cfg = cases.config(case_dict)
     if n_steps is not None:
         cfg = dataclasses.replace(cfg, t_step_stop=cfg.t_step_start + n_steps)
     cb = pre_process.generate_grid(cfg)
-    q0 = pre_process.generate_initial_condition(cfg, cb)
+    q0 = state(cfg, cb) if state is not None else pre_process.generate_initial_condition(cfg, cb)
     return cfg, cb, q0
 
 

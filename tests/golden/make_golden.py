@@ -32,11 +32,18 @@ GOLDEN = {
     "viscous_2d_fd_10": (lambda: cases.viscous_2d(N=29, Nt=10, weno_Re_flux=False), 10),
     "viscous_2d_weno_10": (lambda: cases.viscous_2d(N=29, Nt=10, weno_Re_flux=True), 10),
     "shockbubble_3d_26_6": (lambda: cases.shockbubble_3d(nc=26), 6),
+    # smooth field: all viscous stress terms active (the viscous_2d vectors above never move,
+    # their velocity is piecewise constant)
+    "viscous_wave_2d_weno_20": (lambda: (cases.viscous_wave_2d(N=32, Nx=26, weno_Re_flux=True), cases.viscous_wave_state), 20),
+    "viscous_wave_2d_fd_20": (lambda: (cases.viscous_wave_2d(N=32, Nx=26, weno_Re_flux=False, bc_y=-6), cases.viscous_wave_state), 20),
 }
 
 
 def main():
+    only = sys.argv[1:]
     for name, (mk, n) in GOLDEN.items():
+        if only and name not in only:
+            continue
         cfg, cb, q0 = setup_case(mk(), n_steps=n)
         q, rows = oracle_run(cfg, cb, q0)
         stab = np.array([[r[1]] + [x if x == x else -1.0 for x in r[2]] for r in rows])

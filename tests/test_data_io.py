@@ -31,6 +31,19 @@ def test_parallel_restart_layout_and_round_trip(tmp_path):
     assert all(np.array_equal(a, b) for a, b in zip(data_io.read_grid_parallel(d, cfg), cb))
 
 
+def test_parallel_restart_replaces_a_stale_larger_file(tmp_path):
+    """The reference deletes an existing restart file before writing (MPI_FILE_DELETE,
+    m_data_output.fpp:506-509): a file left by an earlier, larger run must not keep its length."""
+    big = setup_case(cases.shockbubble_2d(Ny=40), n_steps=1)
+    cfg, cb, q0 = setup_case(cases.shockbubble_2d(Ny=30), n_steps=1)
+    d = str(tmp_path)
+    data_io.write_restart_parallel(d, 0, big[2], big[0])
+    data_io.write_restart_parallel(d, 0, q0, cfg)
+    Nz, Ny, Nx = cfg.shape_glb
+    assert os.path.getsize(os.path.join(d, "restart_data", "lustre_0.dat")) == cfg.sys_size * Nx * Ny * 8
+    assert np.array_equal(data_io.read_restart_parallel(d, 0, cfg), q0)
+
+
 def test_parallel_restart_written_by_ranks_equals_single_writer(tmp_path):
     cfg, cb, q0 = setup_case(cases.shockbubble_2d_cells(120, 64), n_steps=1)
     a, b = str(tmp_path / "one"), str(tmp_path / "four")

@@ -46,7 +46,7 @@ def check(cfg, cb, q_ref):
     assert (q == q_ref).mean() > 0.5
 
 
-@pytest.mark.parametrize("name", [n for n in CASES if "weno" not in n or n.startswith("viscous")])
+@pytest.mark.parametrize("name", [n for n in CASES if ("weno" not in n or n.startswith("viscous")) and "viscous_wave" not in n])   # viscous_wave: state not from patches
 def test_device_initial_condition_matches_pre_process(name):
     cfg, cb, q0 = setup_case(CASES[name]())
     check(cfg, cb, q0)

@@ -385,6 +385,34 @@ def test_viscous_shear_wave_decays_at_the_analytic_rate(weno_Re_flux):
     assert abs(rows[0][2][1] - cfg.dt / Re / dx ** 2) < 1e-12
 
 
+@pytest.mark.parametrize("weno_Re_flux,bc_y", [(True, -1), (False, -1), (True, -6), (False, -6)])
+def test_viscous_wave_case_exercises_every_viscous_term(weno_Re_flux, bc_y):
+    """The parity case of the viscous path (cases.viscous_wave_2d, used by tests/test_gpu_parity.py,
+    tests/nccl_worker.py and two golden vectors) must actually be moved by the viscous terms: in
+    examples/2D_viscous the velocity is piecewise constant, the reconstructed gradients of the
+    weno_Re_flux branch are exactly zero and a kernel that did nothing would pass.  Here the
+    viscous run differs from the inviscid run of the same state by several per cent in both
+    momenta and in the energy, and the shear-only / bulk-only runs differ from each other."""
+    def run(keep):
+        d = cases.viscous_wave_2d(N=32, Nx=26, Nt=40, weno_Re_flux=weno_Re_flux, bc_y=bc_y)
+        for k in list(d):
+            if '%Re(' in k and not k.endswith(keep):
+                d.pop(k)
+        cfg = cases.config(d)
+        cb = pre_process.generate_grid(cfg)
+        o = oracle_lib.Oracle(cfg, cb)
+        o.set_q(cases.viscous_wave_state(cfg, cb))
+        oracle_lib.run_p_main(o, cfg)
+        return o.get_q()
+    full, shear, bulk, none = run(")"), run("Re(1)"), run("Re(2)"), run("none")
+    scale = np.abs(none[2:4]).max()
+    for other in (none, shear, bulk):
+        assert np.abs(full[2] - other[2]).max() > 1e-4 * scale       # x-momentum
+        assert np.abs(full[3] - other[3]).max() > 1e-4 * scale       # y-momentum
+    assert np.abs(full[4] - none[4]).max() > 1e-9 * np.abs(none[4]).max()
+    assert np.isfinite(full).all()
+
+
 # ---- 11. order of accuracy ---------------------------------------------------------------------
 @pytest.mark.parametrize("weno_order,time_stepper,err40,order", [
     (5, 3, 5e-6, 4.7),      # WENO5-JS: fifth order
