@@ -71,7 +71,7 @@ struct Sim {
     cudaStream_t cs = nullptr;
     cudaEvent_t ev_q = nullptr, ev_halo[3] = {nullptr, nullptr, nullptr};
     bool halo_pending[3] = {false, false, false};
-    bool overlap = false;
+    bool overlap = false, xsplit_on = false;
     double *state[3] = {nullptr, nullptr, nullptr};
     int cur = 0;                       // which buffer holds q_cons_ts(1)
     const double *last_q = nullptr;    // state of the most recent RHS evaluation (what q_prim_vf reflects)
@@ -422,7 +422,9 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];
         for (int i = 0; i < kNumWenoCoef; i++) a.cuni[i] = S.cuni[d][i];
         // multi-rank, x halo still in flight: sweep the tiles that read no x ghost column first
-        const bool split_x = d == 0 && S.overlap && S.halo_pending[0] && S.nd >= 2;
+        // (optional, MFC_B200_XSPLIT=1: the two boundary strips cost 2 x 32 lane slots per row whatever
+        // their width, ~12 % of a 512-cell row, against ~0.2 ms of exposed x exchange at 512^3)
+        const bool split_x = d == 0 && S.overlap && S.xsplit_on && S.halo_pending[0] && S.nd >= 2;
         if (!split_x && (rc = ghosts_ready(q, d))) return rc;
         {
             const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
@@ -733,6 +735,8 @@ int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
     {
         const char *e = std::getenv("MFC_B200_OVERLAP");       // 0 disables (for A/B measurements)
         S.overlap = !S.viscous && !(e && e[0] == '0');
+        const char *x = std::getenv("MFC_B200_XSPLIT");
+        S.xsplit_on = x && x[0] == '1';
     }
     return 0;
 }

@@ -18,6 +18,13 @@ from microfc_b200 import cases, pre_process  # noqa: E402
 from microfc_b200.simulation import Simulation  # noqa: E402
 from common import norm_linf, oracle_run, setup_case  # noqa: E402
 
+def _advection_64x256():
+    d = cases.advection_2d(N=63)
+    d['n'] = 255
+    d['dt'] = d['dt']*(100.0/256.0)
+    return d
+
+
 CASES = {
     "sod_1d": (lambda: cases.sod_1d(Nx=199), 40),
     "shockbubble_2d": (lambda: cases.shockbubble_2d_cells(120, 64), 25),
@@ -36,7 +43,7 @@ CASES = {
     "viscous_wave_2d_fd": (lambda: (cases.viscous_wave_2d(N=64, Nx=64, weno_Re_flux=False, bc_y=-6), cases.viscous_wave_state), 20),
     # decompositions the reference's rule splits along y / z (m_mpi_proxy.fpp:163-203): the y and z
     # pack / unpack index maps and neighbour tables
-    "shockbubble_2d_ysplit": (lambda: cases.shockbubble_2d_cells(64, 256), 20),               # 2 ranks: 1 x 2
+    "advection_2d_ysplit": (lambda: _advection_64x256(), 20),                                 # 2 ranks: 1 x 2
     "viscous_wave_2d_ysplit": (lambda: (cases.viscous_wave_2d(N=128, Nx=64, weno_Re_flux=True), cases.viscous_wave_state), 10),   # 1 x 2, periodic y, corners
     "shockbubble_3d_ysplit": (lambda: cases.shockbubble_3d(ncx=26, ncy=52, ncz=26), 6),      # 2 ranks: 1 x 2 x 1
     "shockbubble_3d_zsplit": (lambda: cases.shockbubble_3d(ncx=26, ncy=26, ncz=52), 6),      # 2 ranks: 1 x 1 x 2
@@ -75,6 +82,9 @@ def main():
                 ref1, _ = oracle_run(cfg, cb, q0)
                 assert np.array_equal(ref, ref1), "oracle: inviscid result depends on the decomposition"
 
+        # the split x launch (interior cells while the x halo is in flight, then the boundary strips)
+        # is off by default; the wide cases switch it on
+        os.environ["MFC_B200_XSPLIT"] = "1" if "wide" in name else "0"
         for strict in (True, False):
             sim = Simulation(cfg, cb, rank=rank, num_procs=world, strict=strict, device=local, broadcast_id=bcast)
             sim.upload(sim.scatter(q0))
