@@ -156,6 +156,26 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs NVML reports as local to
+    its GPU: with 8 ranks each pushing 9 GB through host memory in the end-to-end leg, buffers on
+    the far socket halve the PCIe rate.  Returns the previous affinity (restored before the CPU
+    baseline, which uses every host core)."""
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (max(prev) // 64) + 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (m >> b) & 1} & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def fp64_peak_in_run(device_index: int):
     """tools/fp64_peak (DFMA micro-benchmark, built by __graft_entry__.build()) on this rank's GPU,
     right before the workload: the FP64 roof of THIS box at THIS moment (MEASURED_PEAKS.json has
@@ -325,6 +345,7 @@ def main():
         return obj[0]
 
     peak_run = fp64_peak_in_run(local_rank) if rank == 0 else None
+    prev_affinity = bind_to_gpu_numa_node(local_rank)
     from microfc_b200.simulation import Simulation
     cb = pre_process.generate_grid(cfg)
     sim = Simulation(cfg, cb, rank=rank, num_procs=world, device=local_rank, broadcast_id=bcast_id if world > 1 else None)
@@ -442,6 +463,8 @@ def main():
     kernel_share = {k: {"seconds": v[0], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
 
     cpu = None
+    if prev_affinity:
+        os.sched_setaffinity(0, prev_affinity)
     if rank == 0 and not args.no_cpu_baseline:
         sample = args.cpu_sample_cells or {3: 128, 2: 1024, 1: 400}[nd]
         r = cpu_reference_run(cfg, 3, 1, sample)

@@ -147,6 +147,16 @@ module m_b200_bindings
             integer(c_int) :: ierr
         end function mfc_b200_generate_initial_condition
 
+        function mfc_b200_generate_initial_condition2(num_patches, patches, cc, cb, ds_min) &
+            bind(C, name='mfc_b200_generate_initial_condition2') result(ierr)
+            import :: c_int, c_int32_t, c_ptr, c_double, mfc_b200_patch_t
+            integer(c_int32_t), value :: num_patches
+            type(mfc_b200_patch_t), intent(in) :: patches(*)
+            type(c_ptr), intent(in) :: cc(3), cb(3)
+            real(c_double), value :: ds_min
+            integer(c_int) :: ierr
+        end function mfc_b200_generate_initial_condition2
+
         function mfc_b200_download(q_cons) bind(C, name='mfc_b200_download') result(ierr)
             import :: c_int, c_ptr
             type(c_ptr), intent(in) :: q_cons(*)
@@ -316,14 +326,16 @@ contains
     !! restart-file round trip + s_b200_upload.  x_cc_pre/y_cc_pre: pre_process' cell centres
     !! (x_cb(i-1) + x_cb(i))/2 of the local cells (m_start_up.fpp:717,743); ds_min: the global
     !! minimum cell width (s_mpi_reduce_min, :720).
-    subroutine s_b200_generate_initial_condition(patch_icpp, num_patches, x_cc_pre, y_cc_pre, ds_min)
+    !! x_cb_pre/y_cb_pre: the right cell boundaries x_cb(0:m), y_cb(0:n), which the analytical
+    !! patches (geometry 7, 15; m_create_patches.fpp:466-467,:527-528) evaluate their bump at.
+    subroutine s_b200_generate_initial_condition(patch_icpp, num_patches, x_cc_pre, y_cc_pre, x_cb_pre, y_cb_pre, ds_min)
         use m_derived_types
         type(ic_patch_parameters), intent(in) :: patch_icpp(:)
         integer, intent(in) :: num_patches
-        real(kind(0d0)), intent(in), target :: x_cc_pre(0:), y_cc_pre(0:)
+        real(kind(0d0)), intent(in), target :: x_cc_pre(0:), y_cc_pre(0:), x_cb_pre(0:), y_cb_pre(0:)
         real(kind(0d0)), intent(in) :: ds_min
         type(mfc_b200_patch_t) :: c(num_patches)
-        type(c_ptr) :: cc(3)
+        type(c_ptr) :: cc(3), cb(3)
         integer :: i, k
         do i = 1, num_patches
             c(i)%geometry = patch_icpp(i)%geometry
@@ -347,8 +359,9 @@ contains
             c(i)%alpha = patch_icpp(i)%alpha(1:MFC_B200_MAX_FLUIDS)
         end do
         cc(1) = c_loc(x_cc_pre); cc(2) = c_loc(y_cc_pre); cc(3) = c_null_ptr
-        call s_b200_check(mfc_b200_generate_initial_condition(int(num_patches, c_int32_t), c, cc, ds_min), &
-                          'mfc_b200_generate_initial_condition')
+        cb(1) = c_loc(x_cb_pre); cb(2) = c_loc(y_cb_pre); cb(3) = c_null_ptr
+        call s_b200_check(mfc_b200_generate_initial_condition2(int(num_patches, c_int32_t), c, cc, cb, ds_min), &
+                          'mfc_b200_generate_initial_condition2')
     end subroutine s_b200_generate_initial_condition
 
     !> p_main.fpp:218,296 and m_time_steppers.fpp:374 -- "!$acc update host(...)"

@@ -32,7 +32,9 @@
 extern "C" {
 #endif
 
-#define MFC_B200_MAX_FLUIDS 4     /* num_fluids_max is 10 in the reference; 4 covers every case */
+#define MFC_B200_MAX_FLUIDS 4     /* array extents of the ABI structs (num_fluids_max is 10 in the reference) */
+#define MFC_B200_BUILT_FLUIDS 2   /* sweep kernels are instantiated for num_fluids = 1, 2 (every shipped example);
+                                     mfc_b200_init fails with MFC_B200_EUNSUPPORTED above that */
 #define MFC_B200_ABI_VERSION 1
 
 enum {
@@ -154,8 +156,9 @@ int mfc_b200_download_prim(double *const q_prim[/*sys_size*/]);
    same on the device, straight into the library's state, and replaces that file round trip +
    mfc_b200_upload for hosts that start from patches: 512^3 x 8 variables per GPU never exist on
    the host.  Fields mirror patch_icpp (src/pre_process/m_global_parameters.fpp:196-230).
-   Geometries: 1 line segment, 2 circle, 3 rectangle, 4 sweep line, 5 ellipse, 18 varcircle;
-   8 sphere, 9 cuboid, 10 z-invariant cylinder are the 3-D extension.  Anything else fails with
+   Geometries: 1 line segment, 15 1-D analytical; 2 circle, 3 rectangle, 4 sweep line, 5 ellipse,
+   6 isentropic vortex, 7 2-D analytical, 18 varcircle (everything m_initial_condition.fpp:50-100
+   dispatches); 8 sphere, 9 cuboid, 10 z-invariant cylinder are the 3-D extension.  Anything else fails with
    MFC_B200_EUNSUPPORTED. */
 #define MFC_B200_MAX_PATCHES 10   /* num_patches_max */
 typedef struct mfc_b200_patch {
@@ -183,6 +186,12 @@ typedef struct mfc_b200_patch {
    as mfc_b200_upload of the generated fields. */
 int mfc_b200_generate_initial_condition(int32_t num_patches, const mfc_b200_patch_t *patches,
                                         const double *const cc[3], double ds_min);
+/* The same with cb[d] = the RIGHT boundaries x_cb(0:m), y_cb(0:n) of this rank's interior cells,
+   which the analytical patches (geometry 7 s_2D_analytical, 15 s_1D_analytical,
+   m_create_patches.fpp:424-534) evaluate their pressure bump at.  cb may be NULL when no such
+   patch is present. */
+int mfc_b200_generate_initial_condition2(int32_t num_patches, const mfc_b200_patch_t *patches,
+                                         const double *const cc[3], const double *const cb[3], double ds_min);
 
 /* p_main.fpp:329-341 -- module finalisers. */
 int mfc_b200_finalize(void);

@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.mfc_b200_compute_rhs.argtypes = [pp, pp]
     L.mfc_b200_download.argtypes = [pp]
     L.mfc_b200_generate_initial_condition.argtypes = [C.c_int32, C.POINTER(Patch), pp, C.c_double]
+    L.mfc_b200_generate_initial_condition2.argtypes = [C.c_int32, C.POINTER(Patch), pp, pp, C.c_double]
     L.mfc_b200_download_prim.argtypes = [pp]
     L.mfc_b200_finalize.argtypes = []
     L.mfc_b200_last_error.restype = C.c_char_p
@@ -127,5 +128,5 @@ EXPORTED_SYMBOLS = [
     "mfc_b200_download", "mfc_b200_download_prim", "mfc_b200_finalize", "mfc_b200_last_error",
     "mfc_b200_get_weno_coefficients", "mfc_b200_kernel_launches", "mfc_b200_state_snapshot",
     "mfc_b200_state_restore", "mfc_b200_timer_start", "mfc_b200_timer_stop", "mfc_b200_profile_enable", "mfc_b200_profile_get", "mfc_b200_kernel_name",
-    "mfc_b200_generate_initial_condition", "mfc_b200_debug_fill_ghosts",
+    "mfc_b200_generate_initial_condition", "mfc_b200_generate_initial_condition2", "mfc_b200_debug_fill_ghosts",
 ]

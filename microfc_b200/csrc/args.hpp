@@ -57,6 +57,10 @@ struct SweepArgs {
     // viscous runs only (else nullptr): the sweep stores vel_src (nd planes) and Re_avg (2 planes)
     // of every face it solves, for k_visc (m_riemann_solvers.fpp:225-230,314-324)
     double *visc_face;
+    // fast build, weno_Re_flux = F (visc_mode 2): the viscous source flux is computed inside the sweeps
+    // from rdcc = 1/(s_cc(i+1) - s_cc(i)) of this direction and the per-cell gradient planes of k_vgrad
+    int visc_mode;               // 0 inviscid, 1 face planes for k_visc, 2 in-sweep
+    const double *rdcc, *vgrad;
     double Res[2][kMaxFluids];
     double iRes[2][kMaxFluids];  // 1/Res (fast build: the face stores 1/Re_avg, no divisions)
     int Re_idx[2][kMaxFluids], Re_size[2];
@@ -135,6 +139,7 @@ struct PatchArgs {
     GridDesc g;
     double *q;                 // state planes (conservative variables are written to the interior)
     const double *cc[3];       // pre_process cell centres of this rank's interior cells, N_d + 1 doubles
+    const double *cb[3];       // their right boundaries s_cb(0:N_d) (analytical patches 7, 15), or nullptr
     const PatchDesc *patches;  // device copy, num_patches entries in patch order
     int num_patches;
     double ds_min;             // min(dx, dy[, dz]) over the GLOBAL grid (s_mpi_reduce_min, m_start_up.fpp:720)
@@ -162,6 +167,7 @@ struct Launchers {
     int (*stability)(int nf, int nd, const StabArgs &, cudaStream_t);
     int (*visc_grad)(int nd, const ViscArgs &, cudaStream_t);
     int (*visc)(int nd, const ViscArgs &, cudaStream_t);
+    int (*vgrad)(int nd, const ViscArgs &, cudaStream_t);
 };
 const Launchers &launchers_fast();
 const Launchers &launchers_strict();

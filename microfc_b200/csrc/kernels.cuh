@@ -388,6 +388,81 @@ __device__ __forceinline__ void store_visc_face(const SweepArgs &a, unsigned off
     a.visc_face[(ND + 1)*fs + off] = Re_avg[1];
 }
 
+// Fast build, weno_Re_flux = F: the viscous source flux of one face of direction ID
+// (m_riemann_solvers.fpp:683-902 with the finite-difference gradients of m_viscous.fpp:219-347),
+// computed INSIDE the sweep right after the Riemann solve and folded into the flux, so that the
+// flux difference of m_rhs.fpp:565-653 carries the viscous terms of :591-604, :639-652 with it: no
+// face planes, no separate pass, and the TVD-RK statement stays fused into the last sweep.
+//   dn[v] = d vel_v / d x_ID at the face (difference of the two cell centres, m_viscous.fpp:224-248)
+//   ct[v] = d vel_v / d x_other at the face = mean of the two cells' averaged one-sided differences
+//           (:278-347), which k_vgrad prepared per cell
+//   vs    = vel_src of the face (m_riemann_solvers.fpp:314-324), L / R = the face states (alpha for Re)
+template <int NF, int ND, int ID>
+__device__ __forceinline__ void visc_flux_fd(const SweepArgs &a, const double *L, const double *R, const double *vs,
+                                             const double *dn, const double *ct, double *F) {
+    constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1, O = ND > 1 ? 1 - ID : 0;
+    double iRe[2];                                     // 1/Re_avg = (1/Re_L + 1/Re_R)/2, :169-200, :225-230
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double rl = a.Re_size[i] > 0 ? 0.0 : -1e6, rr = rl;
+        for (int q = 0; q < a.Re_size[i]; q++) {
+            double al = L[ADV], ar = R[ADV];
+#pragma unroll
+            for (int f = 1; f < NF; f++)
+                if (a.Re_idx[i][q] == f) { al = L[ADV + f]; ar = R[ADV + f]; }
+            rl = fma(al, a.iRes[i][q], rl);
+            rr = fma(ar, a.iRes[i][q], rr);
+        }
+        iRe[i] = 0.5*(fmax(rl, 1e-16) + fmax(rr, 1e-16));
+    }
+    double avg[ND > 1 ? 2 : 1][ND];                    // avg[dd][v] = d vel_v / d x_dd
+#pragma unroll
+    for (int v = 0; v < ND; v++) {
+        avg[ND > 1 ? ID : 0][v] = dn[v];
+        if (ND > 1) avg[O][v] = ct[v];
+    }
+    double m[ND], e = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) m[i] = 0.0;
+    constexpr int Y = ND > 1 ? 1 : 0;
+    if (ID == 0) {
+        if (a.Re_size[0] > 0) {                        // :714-736
+            const double tau = (4.0/3.0)*avg[0][0]*iRe[0];
+            m[0] -= tau; e = fma(-vs[0], tau, e);
+        }
+        if (a.Re_size[1] > 0) {                        // :738-760
+            const double tau = avg[0][0]*iRe[1];
+            m[0] -= tau; e = fma(-vs[0], tau, e);
+        }
+        if (ND > 1) {
+            if (a.Re_size[0] > 0) {                    // :764-801
+                const double t0 = -(2.0/3.0)*avg[Y][Y]*iRe[0];
+                const double t1 = (avg[Y][0] + avg[0][Y])*iRe[0];
+                m[0] -= t0; e = fma(-vs[0], t0, e);
+                m[Y] -= t1; e = fma(-vs[Y], t1, e);
+            }
+            if (a.Re_size[1] > 0) {                    // :803-825
+                const double tau = avg[Y][Y]*iRe[1];
+                m[0] -= tau; e = fma(-vs[0], tau, e);
+            }
+        }
+    } else {
+        if (a.Re_size[0] > 0) {                        // :831-872
+            const double t0 = (avg[Y][0] + avg[0][Y])*iRe[0];
+            const double t1 = (4.0*avg[Y][Y] - 2.0*avg[0][0])*((1.0/3.0)*iRe[0]);
+            m[0] -= t0; e = fma(-vs[0], t0, e);
+            m[Y] -= t1; e = fma(-vs[Y], t1, e);
+        }
+        if (a.Re_size[1] > 0) {                        // :874-899
+            const double tau = (avg[0][0] + avg[Y][Y])*iRe[1];
+            m[Y] -= tau; e = fma(-vs[Y], tau, e);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ND; i++) F[MOM + i] += m[i];
+    F[EN] += e;
+}
+
 __device__ __forceinline__ void load_coef(const SweepArgs &a, int cell, double c[27]) {
     const double *p = a.coef + (cell - a.coef_lo);
 #pragma unroll
@@ -708,8 +783,9 @@ __device__ __forceinline__ void finish_cell2(const SweepArgs &a, unsigned off, b
 // unit wants 16-byte aligned starts; the part of a box before a row's first ghost column is
 // zero-filled and read by no lane that stores), and a lane picks the slot of its own row.
 // No block-wide barrier exists, so warps never wait for each other.
-// BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).  VISC: viscous run,
-// vel_src and Re_avg of every face are stored for k_visc.
+// BC4: some side of this direction has bc = -4 (Riemann-state extrapolation).  VISC = 1: viscous run,
+// vel_src and Re_avg of every face are stored for k_visc; VISC = 2 (fast build, weno_Re_flux = F): the
+// viscous source flux is computed here and folded into the flux (visc_flux_fd).
 // ------------------------------------------------------------------------------------------
 constexpr int kPrimRing = 40;                      // entries of the primitive ring (>= 32 + 4, multiple of 8)
 constexpr int kXchRing = 33;                       // entries of the exchange rings (32 lanes + the carried one)
@@ -764,7 +840,7 @@ __device__ __forceinline__ void prim_regs(double (&q)[2*NF + ND + 1], const doub
 #endif
 }
 
-template <int NF, int ND, int COEF, bool BC4, bool VISC, int WO>
+template <int NF, int ND, int COEF, bool BC4, int VISC, int WO>
 __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = slot_doubles(E, kWX);
     constexpr int PR = kPrimRing, XR = kXchRing;
@@ -884,6 +960,16 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_con
         const double rds = a.rds[max(jf, 0) + g.b];
         CellIn<E, ACC, RK> in;
         if (RK) load_cell<NF, ND, ACC, RK>(a, off, in);
+        // VISC == 2: the transverse velocity gradients of the face's two cells (planes [1][v] of
+        // k_vgrad), requested here so that the loads fly under the reconstruction
+        double vg_l[ND > 1 ? ND : 1], vg_r[ND > 1 ? ND : 1];
+        if (VISC == 2 && ND > 1) {
+#pragma unroll
+            for (int v = 0; v < ND; v++) {
+                const double *pl = a.vgrad + (size_t)(ND + v)*g.fstride + off;
+                vg_l[v] = __ldg(pl); vg_r[v] = __ldg(pl + 1);
+            }
+        }
         double vL[E], vR[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
@@ -933,8 +1019,18 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_con
         double vs[ND];
         hllc<NF, ND, 0>(Lst, vL, a.gammas, a.pi_infs, F, uf, vs);
         // faces ja-1/2 .. jb+1/2, keyed by the left cell (entry g-3; both entries lie in one row there)
-        if (VISC && row3_ok && il3 >= 2 && il3 <= Lt - 4)
+        if (VISC == 1 && row3_ok && il3 >= 2 && il3 <= Lt - 4)
             store_visc_face<NF, ND>(a, off, Lst, vL, vs);
+        if (VISC == 2) {                               // viscous source flux of this face, folded into F
+            double dn[ND], ct[ND];
+            const double rd = __ldg(a.rdcc + max(jf, -1) + g.b);   // 1/(x_cc(j3+1) - x_cc(j3))
+#pragma unroll
+            for (int v = 0; v < ND; v++) {
+                dn[v] = (prim[(NF + v)*PR + tp[2]] - prim[(NF + v)*PR + tp[1]])*rd;
+                ct[v] = ND > 1 ? 0.5*(vg_l[v] + vg_r[v]) : 0.0;
+            }
+            visc_flux_fd<NF, ND, 0>(a, Lst, vL, vs, dn, ct, F);
+        }
         // ---- entry g-3: finish --------------------------------------------------------------------
 #pragma unroll
         for (int v = 0; v < E; v++) xf[v*XR + wpos] = F[v];
@@ -978,7 +1074,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_con
 // per cell become 24 LDS/STS.  The only synchronisation is the mbarrier wait and a __syncwarp
 // before a slot is handed back.  Lanes beyond the domain compute on zero-filled columns.
 // ------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR, int COEF, bool BC4, bool VISC, int WO>
+template <int NF, int ND, int DIR, int COEF, bool BC4, int VISC, int WO>
 __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
@@ -1061,6 +1157,16 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
         if (!AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
         off += uss;
         weno.load(a, s);
+        // VISC == 2: the x gradients of the velocities (planes [0][v] of k_vgrad) of cells s-1 and s of
+        // my column, requested here so that the loads fly under the reconstruction
+        double vg_l[ND], vg_r[ND];
+        if (VISC == 2) {
+#pragma unroll
+            for (int v = 0; v < ND; v++) {
+                const double *pl = a.vgrad + (size_t)v*g.fstride + off;
+                vg_l[v] = __ldg(pl); vg_r[v] = __ldg(pl + uss);
+            }
+        }
         double vL[E], vRn[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
@@ -1107,7 +1213,17 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
             double vs[ND];
             if (AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
             hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Fn, ufn, vs);
-            if (VISC && on && s >= s0) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
+            if (VISC == 1 && on && s >= s0) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
+            if (VISC == 2) {                           // viscous source flux of face s-1/2, folded into Fn
+                double dn[ND], ct[ND];
+                const double rd = __ldg(a.rdcc + s - 1 + g.b);       // 1/(s_cc(s) - s_cc(s-1))
+#pragma unroll
+                for (int v = 0; v < ND; v++) {
+                    dn[v] = (p2[(NF + v)*kWY] - p1[(NF + v)*kWY])*rd;   // rows s, s-1
+                    ct[v] = 0.5*(vg_l[v] + vg_r[v]);
+                }
+                visc_flux_fd<NF, ND, DIR>(a, L, vL, vs, dn, ct, Fn);
+            }
             if (fin) {
                 double y[E];
                 finish_vals<NF, ND, kWY, ACC, RK>(a, a.rds[s - 1 + g.b], p1, in, Fp, ufp, Fn, ufn, y);   // p1: row s-1
@@ -1346,6 +1462,43 @@ __device__ __forceinline__ void weno_at(const double *f, long long cell, long lo
 #pragma unroll
     for (int q = 0; q < 5; q++) st[q] = f[cell + (long long)(q - 2)*stride];
     weno5(st, c, eps, vL, vR);
+}
+
+// Fast build, weno_Re_flux = F: per cell and direction dd the mean of the two one-sided differences
+// of every velocity, C[dd][v] = ((u_c - u_{c-1})/(cc_c - cc_{c-1}) + (u_{c+1} - u_c)/(cc_{c+1} - cc_c))/2
+// (m_viscous.fpp:278-347: the cross-direction gradient of a face is the mean of its two cells' C).
+// Cells -1 .. N+1 of both directions (the faces of direction d reach one cell into its ghosts).
+// The velocities come straight from the conservative state (momentum / max(rho, sgm_eps),
+// m_variables_conversion.fpp:353-359): no primitive planes are written on this path.
+template <int NF, int ND>
+__global__ void __launch_bounds__(128) k_vgrad(const __grid_constant__ ViscArgs a) {
+    const GridDesc &g = a.g;
+    const int j = (int)(blockIdx.y*blockDim.x + threadIdx.x) - 1;
+    const int k = ND > 1 ? (int)blockIdx.x - 1 : 0;
+    if (j > g.N[0] + 1) return;
+    const int c[3] = {j, k, 0};
+    const long long cell = g.at(j, k, 0), fs = g.fstride;
+    auto vel = [&](long long at, double (&u)[ND]) {
+        double rho = a.qs[at];
+#pragma unroll
+        for (int i = 1; i < NF; i++) rho += a.qs[i*fs + at];
+        const double ir = rcp_fast3(fmax(rho, 1e-16));
+#pragma unroll
+        for (int v = 0; v < ND; v++) u[v] = a.qs[(NF + v)*fs + at]*ir;
+    };
+    double u0[ND];
+    vel(cell, u0);
+#pragma unroll
+    for (int dd = 0; dd < ND; dd++) {
+        const long long sd = g.stride(dd);
+        const double rm = a.rdcc[dd][c[dd] - 1 + g.b], rp = a.rdcc[dd][c[dd] + g.b];
+        double um[ND], up[ND];
+        vel(cell - sd, um);
+        vel(cell + sd, up);
+#pragma unroll
+        for (int v = 0; v < ND; v++)
+            a.grad[(dd*ND + v)*fs + cell] = 0.5*((u0[v] - um[v])*rm + (up[v] - u0[v])*rp);
+    }
 }
 
 // weno_Re_flux branch, m_viscous.fpp:186-217: velocities are WENO-reconstructed along every

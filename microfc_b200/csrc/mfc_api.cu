@@ -64,6 +64,7 @@ struct Sim {
     GridDesc g{};
     int nf = 0, nd = 0, E = 0, b = 0;
     bool viscous = false;
+    bool visc_fused = false;           // fast build, weno_Re_flux = F: viscous fluxes inside the sweeps
     const Launchers *L = nullptr;
     cudaStream_t st = nullptr;
     // multi-rank: the halo exchange runs on its own stream so that the y / z exchanges overlap
@@ -373,8 +374,9 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
     // m_rhs.fpp:435.  Anything that reads the whole ghosted box needs every direction complete.
     const bool need_all = stop || S.viscous;
     if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
-    // :445-447 (fused into the sweeps; the viscous kernels read the velocity planes)
-    if (S.viscous && (rc = run_prim(q))) return rc;
+    // :445-447 (fused into the sweeps; the viscous kernels read the velocity planes -- the in-sweep
+    // viscous path only needs them for the cross-direction gradients, i.e. not in 1-D)
+    if (S.viscous && (!S.visc_fused || stop) && (rc = run_prim(q))) return rc;
     if (stop) return 0;                                      // m_rhs.fpp:452, m_time_steppers.fpp:296
     S.last_q = q;
     // m_time_steppers.fpp:288-290.  Inviscid fast build: the ICFL maximum is taken by the x sweep
@@ -399,6 +401,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         va.eps = S.p.weno_eps; va.nf = S.nf; va.weno_Re_flux = S.p.weno_Re_flux;
         va.Re_size[0] = S.Re_size[0]; va.Re_size[1] = S.Re_size[1];
         if (S.p.weno_Re_flux) { Scope sc(KC_VISC); sc.done(S.L->visc_grad(S.nd, va, S.st)); }
+        if (S.visc_fused && S.nd > 1) { Scope sc(KC_VISC); sc.done(S.L->vgrad(S.nd, va, S.st)); }
     }
     for (int d = 0; d < S.nd; d++) {                         // :469
         SweepArgs a{};
@@ -408,8 +411,10 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         for (int i = 0; i < kMaxFluids; i++) { a.gammas[i] = S.p.gammas[i]; a.pi_infs[i] = S.p.pi_infs[i]; }
         a.bc_beg = S.p.bc[2*d]; a.bc_end = S.p.bc[2*d + 1];
         a.first_dir = d == 0;
-        a.rk_mode = (d == S.nd - 1 && !S.viscous) ? rk_mode : 0;
-        a.visc_face = S.viscous ? S.visc_face : nullptr;
+        a.rk_mode = (d == S.nd - 1 && (!S.viscous || S.visc_fused)) ? rk_mode : 0;
+        a.visc_mode = S.viscous ? (S.visc_fused ? 2 : 1) : 0;
+        a.visc_face = a.visc_mode == 1 ? S.visc_face : nullptr;
+        a.rdcc = S.rdcc[d]; a.vgrad = S.visc_grad;
         for (int i = 0; i < 2; i++) {
             a.Re_size[i] = S.Re_size[i];
             for (int k = 0; k < kMaxFluids; k++) {
@@ -451,7 +456,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         }
         sc.done(n);
         if (fuse_stab && d == 0 && (rc = stab_reduce_and_copy())) return rc;
-        if (S.viscous) {                                     // m_rhs.fpp:591-604, :639-652
+        if (S.viscous && !S.visc_fused) {                    // m_rhs.fpp:591-604, :639-652
             va.dir = d; va.bc_beg = S.p.bc[2*d]; va.bc_end = S.p.bc[2*d + 1];
             // the RK statement cannot be fused into the last sweep (the viscous terms come after
             // it); it is applied by the last direction's k_visc, which completes the RHS
@@ -572,6 +577,9 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     if (nd < 1 || nd > 3) return fail(MFC_B200_EINVAL, "Unsupported value of num_dims");
     if (nf < 1 || nf > MFC_B200_MAX_FLUIDS)
         return fail(MFC_B200_EINVAL, "Unsupported value of num_fluids (kernels are instantiated for 1.." + std::to_string(MFC_B200_MAX_FLUIDS) + " fluids). Exiting ...");
+    if (nf > MFC_B200_BUILT_FLUIDS)
+        return fail(MFC_B200_EUNSUPPORTED, "num_fluids = " + std::to_string(nf) + ": the sweep kernels are instantiated for 1.." +
+                                           std::to_string(MFC_B200_BUILT_FLUIDS) + " fluids (MFC_DISPATCH in kernels_inst.inc)");
     if (p->sys_size != 2*nf + nd + 1) return fail(MFC_B200_EINVAL, "sys_size /= 2*num_fluids + num_dims + 1");
     if (p->m <= 0) return fail(MFC_B200_EINVAL, "Unsupported value of m. Exiting ...");
     if (p->n < 0 || (nd > 1) != (p->n > 0)) return fail(MFC_B200_EINVAL, "Unsupported value of n. Exiting ...");
@@ -613,6 +621,10 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
     for (int d = 0; d < 3; d++) S.p.cb[d] = S.p.cc[d] = S.p.ds[d] = nullptr;    // never keep host pointers
     S.nf = nf; S.nd = nd; S.E = p->sys_size; S.b = p->buff_size; S.viscous = visc;
     S.L = p->strict_math ? &launchers_strict() : &launchers_fast();
+    {
+        const char *e = std::getenv("MFC_B200_VISC_FUSED");    // 0: keep the separate k_visc pass (A/B measurements)
+        S.visc_fused = visc && !p->strict_math && !p->weno_Re_flux && !(e && e[0] == '0');
+    }
     S.Re_size[0] = S.Re_size[1] = 0;                                   // m_global_parameters.fpp:314-339, m_rhs.fpp:385-390
     for (int i = 0; i < nf; i++)
         for (int k = 0; k < 2; k++)
@@ -754,15 +766,24 @@ int mfc_b200_upload(const double *const q_cons[]) {
 
 int mfc_b200_generate_initial_condition(int32_t num_patches, const mfc_b200_patch_t *patches,
                                         const double *const cc[3], double ds_min) {
+    return mfc_b200_generate_initial_condition2(num_patches, patches, cc, nullptr, ds_min);
+}
+
+int mfc_b200_generate_initial_condition2(int32_t num_patches, const mfc_b200_patch_t *patches,
+                                         const double *const cc[3], const double *const cb[3], double ds_min) {
     if (!S.inited) return fail(MFC_B200_ESTATE, "mfc_b200_generate_initial_condition before mfc_b200_init");
     if (num_patches < 1 || num_patches > MFC_B200_MAX_PATCHES || !patches || !cc)
         return fail(MFC_B200_EINVAL, "num_patches must be 1..MFC_B200_MAX_PATCHES with non-NULL arrays");
     static_assert(sizeof(PatchDesc) == sizeof(mfc_b200_patch_t), "PatchDesc mirrors mfc_b200_patch_t");
     for (int i = 0; i < num_patches; i++) {
         const int geo = patches[i].geometry;
-        const bool ok = geo == 1 || ((geo == 2 || geo == 3 || geo == 4 || geo == 5 || geo == 18) && S.nd >= 2) ||
+        // m_initial_condition.fpp:50-100: 1, 15 in 1-D; 2..7, 18 in 2-D; 8, 9, 10 are the 3-D extension
+        const bool ok = ((geo == 1 || geo == 15) && S.nd == 1) || (geo == 1 && S.nd > 1) ||
+                        ((geo == 2 || geo == 3 || geo == 4 || geo == 5 || geo == 6 || geo == 7 || geo == 18) && S.nd >= 2) ||
                         ((geo == 8 || geo == 9 || geo == 10) && S.nd == 3);
         if (!ok) return fail(MFC_B200_EUNSUPPORTED, "patch geometry " + std::to_string(geo) + " is not built for this num_dims");
+        if ((geo == 7 || geo == 15) && !cb)
+            return fail(MFC_B200_EINVAL, "analytical patches (geometry 7, 15) need the cell boundaries: call mfc_b200_generate_initial_condition2 with cb");
         if (patches[i].smooth_patch_id < 0 || patches[i].smooth_patch_id > num_patches)
             return fail(MFC_B200_EINVAL, "smooth_patch_id out of range");
     }
@@ -775,7 +796,7 @@ int mfc_b200_generate_initial_condition(int32_t num_patches, const mfc_b200_patc
     size_t used = 0;
     for (int d = 0; d < S.nd; d++) {
         if (!cc[d]) return fail(MFC_B200_EINVAL, "cc[d] is NULL for an active direction");
-        used += ((size_t)g.N[d] + 1 + 15)/16*16;
+        used += 2*(((size_t)g.N[d] + 1 + 15)/16*16);
     }
     if (used*sizeof(double) + (size_t)num_patches*sizeof(PatchDesc) > field_bytes()*S.E)
         return fail(MFC_B200_ENOMEM, "grid too small to stage the patch table");
@@ -785,6 +806,12 @@ int mfc_b200_generate_initial_condition(int32_t num_patches, const mfc_b200_patc
         const size_t n = (size_t)g.N[d] + 1;
         CK(cudaMemcpyAsync(scr + used, cc[d], n*sizeof(double), cudaMemcpyHostToDevice, S.st));
         a.cc[d] = scr + used;
+        used += (n + 15)/16*16;
+        a.cb[d] = nullptr;
+        if (cb && cb[d]) {
+            CK(cudaMemcpyAsync(scr + used, cb[d], n*sizeof(double), cudaMemcpyHostToDevice, S.st));
+            a.cb[d] = scr + used;
+        }
         used += (n + 15)/16*16;
     }
     CK(cudaMemcpyAsync(pd, patches, (size_t)num_patches*sizeof(PatchDesc), cudaMemcpyHostToDevice, S.st));

@@ -7,9 +7,9 @@
 // planes -- 512^3 x 8 variables never exist on the host.
 //
 // Built with -fmad=false: every expression is evaluated in the order the Fortran statements
-// are written.  tanh comes from the CUDA math library (<= 2 ulp from glibc / numpy), so cells in
-// a smoothed patch boundary may differ from a host pre_process in the last bits; hard-edged
-// patches are bit-identical.  Citations relative to /root/reference/src/pre_process.
+// are written.  tanh / exp come from the CUDA math library (<= 2 ulp from glibc / numpy), so cells in
+// a smoothed patch boundary or an analytical patch (geometry 7, 15) may differ from a host
+// pre_process in the last bits; hard-edged patches are bit-identical.  Citations relative to /root/reference/src/pre_process.
 #include <cuda_runtime.h>
 #include "args.hpp"
 
@@ -22,6 +22,12 @@ __device__ __forceinline__ void patch_geometry(const PatchDesc &pt, double X, do
     smoothable = false;
     inside = false;
     switch (pt.geometry) {
+    case 6: {                                        // s_isentropic_vortex, m_create_patches.fpp:379-419: a hard circle
+        const double dx = X - pt.x_centroid, dy = Y - pt.y_centroid;
+        inside = dx*dx + dy*dy <= pt.radius*pt.radius;
+        break;
+    }
+    case 15:                                         // s_1D_analytical, :424-473 (+ the pressure bump, see the caller)
     case 1: {                                        // s_line_segment, m_create_patches.fpp:47-88
         const double xb = pt.x_centroid - 0.5*pt.length_x, xe = pt.x_centroid + 0.5*pt.length_x;
         inside = xb <= X && xe >= X;
@@ -49,6 +55,7 @@ __device__ __forceinline__ void patch_geometry(const PatchDesc &pt, double X, do
         inside = r2 <= 1.0;
         break;
     }
+    case 7:                                          // s_2D_analytical, :479-534 (+ the pressure bump, see the caller)
     case 3: {                                        // s_rectangle, :262-313
         const double xb = pt.x_centroid - 0.5*pt.length_x, xe = pt.x_centroid + 0.5*pt.length_x;
         const double yb = pt.y_centroid - 0.5*pt.length_y, ye = pt.y_centroid + 0.5*pt.length_y;
@@ -115,6 +122,14 @@ __global__ void __launch_bounds__(128) k_patches(const __grid_constant__ PatchAr
 #pragma unroll
         for (int d = 0; d < ND; d++) q[MOM + d] = eta*pt.vel[d] + ome*q[MOM + d];   // :149-153
         q[EN] = eta*pt.pres + ome*q[EN];                             // :156-158
+        if (pt.geometry == 15 || pt.geometry == 7) {
+            // the analytical patches multiply the pressure by a Gaussian bump evaluated at the RIGHT
+            // cell boundaries x_cb(i), y_cb(j) (m_create_patches.fpp:466-467, :527-528)
+            const double tx = a.cb[0][j] - pt.x_centroid;
+            double r2 = tx*tx;
+            if (pt.geometry == 7) { const double ty = a.cb[ND > 1 ? 1 : 0][k] - pt.y_centroid; r2 = r2 + ty*ty; }
+            q[EN] = q[EN]*(1.0 + 0.2*exp(-1.0*r2/(2.0*0.005)));
+        }
         if (ome < 1e-16) patch_id = i + 1;                           // :163
     }
     // s_convert_primitive_to_conservative_variables, src/common/m_variables_conversion.fpp:385-443

@@ -74,6 +74,12 @@ def generate_initial_condition(cfg: CaseConfig, cb_glb: List[np.ndarray], box=No
     X = cc[0].reshape(1, 1, Nx)
     Y = cc[1].reshape(1, Ny, 1) if nd > 1 else np.zeros((1, 1, 1))
     Z = cc[2].reshape(Nz, 1, 1) if nd > 2 else np.zeros((1, 1, 1))
+    # right cell boundaries x_cb(0:m) (the analytical patches evaluate their bump at x_cb(i), not x_cc(i))
+    cbr = [cb_glb[d][1:] for d in range(nd)]
+    if box is not None:
+        cbr = [cbr[d][box[2 - d]] for d in range(nd)]
+    XB = cbr[0].reshape(1, 1, Nx)
+    YB = cbr[1].reshape(1, Ny, 1) if nd > 1 else np.zeros((1, 1, 1))
     dmin_all = min(dmin)                                         # min(dx, dy) in the smoothing formulas
     shape = (Nz, Ny, Nx)
     contxe, momxb, E_idx, advxb = nf, nf, nf + nd, nf + nd + 1    # 0-based starts / exclusive ends
@@ -85,7 +91,19 @@ def generate_initial_condition(cfg: CaseConfig, cb_glb: List[np.ndarray], box=No
         geo = pt.geometry
         eta = np.ones(shape)
         smoothable = False
-        if geo == 1:                                             # s_line_segment, m_create_patches.fpp:47-88
+        pres_factor = None                                       # analytical patches: pressure bump
+        if geo == 6:                                             # s_isentropic_vortex, m_create_patches.fpp:379-419: a hard circle
+            inside = np.broadcast_to((X - pt.x_centroid) ** 2 + (Y - pt.y_centroid) ** 2 <= pt.radius ** 2, shape)
+        elif geo == 15:                                          # s_1D_analytical, :424-473
+            xb, xe = pt.x_centroid - 0.5 * pt.length_x, pt.x_centroid + 0.5 * pt.length_x
+            inside = np.broadcast_to((xb <= X) & (xe >= X), shape)
+            pres_factor = np.broadcast_to(1.0 + 0.2 * np.exp(-1.0 * ((XB - pt.x_centroid) ** 2) / (2.0 * 0.005)), shape)   # :466-467
+        elif geo == 7:                                           # s_2D_analytical, :479-534
+            xb, xe = pt.x_centroid - 0.5 * pt.length_x, pt.x_centroid + 0.5 * pt.length_x
+            yb, ye = pt.y_centroid - 0.5 * pt.length_y, pt.y_centroid + 0.5 * pt.length_y
+            inside = np.broadcast_to((xb <= X) & (xe >= X) & (yb <= Y) & (ye >= Y), shape)
+            pres_factor = np.broadcast_to(1.0 + 0.2 * np.exp(-1.0 * ((XB - pt.x_centroid) ** 2 + (YB - pt.y_centroid) ** 2) / (2.0 * 0.005)), shape)   # :527-528
+        elif geo == 1:                                             # s_line_segment, m_create_patches.fpp:47-88
             xb, xe = pt.x_centroid - 0.5 * pt.length_x, pt.x_centroid + 0.5 * pt.length_x
             inside = np.broadcast_to((xb <= X) & (xe >= X), shape)
         elif geo == 2 or geo == 10:                              # s_circle, :96-146 (10: z-invariant cylinder)
@@ -152,6 +170,8 @@ def generate_initial_condition(cfg: CaseConfig, cb_glb: List[np.ndarray], box=No
         for i in range(nd):
             q_prim[momxb + i] = np.where(mask, blend(pt.vel[i], orig[momxb + i]), q_prim[momxb + i])
         q_prim[E_idx] = np.where(mask, blend(pt.pres, orig[E_idx]), q_prim[E_idx])
+        if pres_factor is not None:
+            q_prim[E_idx] = np.where(mask, q_prim[E_idx] * pres_factor, q_prim[E_idx])
         patch_id_fp = np.where(mask & (one_m_eta < 1e-16), pid, patch_id_fp)    # :163
 
     return prim_to_cons(cfg, q_prim)

@@ -157,10 +157,13 @@ class Simulation:
         minimum cell width (s_mpi_reduce_min, :720)."""
         arr = patch_array(self.cfg)
         cc, ds_min = rank_cell_centres(self.cfg, self.layout, cb_glb)
-        ptrs = (abi.c_double_p * 3)()
+        zs, ys, xs = self.layout.interior_slices()
+        cbr = [np.ascontiguousarray(cb_glb[d][1:][(xs, ys, zs)[d]]) for d in range(self.cfg.num_dims)]   # x_cb(0:m), ...
+        ptrs, bptrs = (abi.c_double_p * 3)(), (abi.c_double_p * 3)()
         for d, c in enumerate(cc):
             ptrs[d] = c.ctypes.data_as(abi.c_double_p)
-        abi.check(self.L.mfc_b200_generate_initial_condition(len(arr), arr, ptrs, ds_min))
+            bptrs[d] = cbr[d].ctypes.data_as(abi.c_double_p)
+        abi.check(self.L.mfc_b200_generate_initial_condition2(len(arr), arr, ptrs, bptrs, ds_min))
 
     def upload_ghosted(self, q_ghosted: np.ndarray) -> None:
         assert q_ghosted.shape == (self.E,) + self.ghost_shape and q_ghosted.dtype == np.float64

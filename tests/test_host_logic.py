@@ -229,3 +229,51 @@ def test_rank_cell_centres_tile_the_global_grid():
         assert ds_min == min(float(np.min(c[1:] - c[:-1])) for c in cb)      # GLOBAL minimum on every rank
     for d in range(3):
         assert np.array_equal(got[d], glb[d])
+
+
+def test_analytical_and_vortex_patches_of_the_host_pre_process():
+    """Geometries 6, 7, 15 (m_create_patches.fpp:379-534) in microfc_b200/pre_process.py: 6 is a hard
+    circle; 7 / 15 are a rectangle / line segment whose pressure carries the factor
+    1 + 0.2 exp(-((x_cb(i) - xc)^2 [+ (y_cb(j) - yc)^2]) / (2 * 0.005)), evaluated at the RIGHT cell
+    boundaries (not the centres)."""
+    import dataclasses
+    import numpy as np
+    from microfc_b200 import cases, pre_process
+    # 1-D, geometry 15 against geometry 1 of the same extent
+    base = cases.config(cases.sod_1d(Nx=99))
+    ps = [dataclasses.replace(p) for p in base.patches]
+    ps[0].geometry = 15
+    cfg = dataclasses.replace(base, patches=ps)
+    cb = pre_process.generate_grid(cfg)
+    q15 = pre_process.generate_initial_condition(cfg, cb)
+    q1 = pre_process.generate_initial_condition(base, cb)
+    xc = ps[0].x_centroid
+    x_cc = (cb[0][1:] + cb[0][:-1]) / 2
+    inside = (x_cc >= xc - 0.5 * ps[0].length_x) & (x_cc <= xc + 0.5 * ps[0].length_x)
+    factor = np.where(inside, 1.0 + 0.2 * np.exp(-((cb[0][1:] - xc) ** 2) / 0.01), 1.0)
+    gam = cfg.gamma[0]
+    p1 = (q1[2, 0, 0] - 0.5 * q1[1, 0, 0] ** 2 / q1[0, 0, 0]) / gam
+    p15 = (q15[2, 0, 0] - 0.5 * q15[1, 0, 0] ** 2 / q15[0, 0, 0]) / gam
+    assert np.allclose(p15, p1 * factor, rtol=1e-13)
+    assert np.array_equal(q15[0], q1[0]) and np.array_equal(q15[3], q1[3])
+    # 2-D: geometry 6 == geometry 2 without smoothing; geometry 7 == geometry 3 times the bump
+    b2 = cases.config(cases.advection_2d(N=39))
+    for geo_a, geo_b in ((6, 2), (7, 3)):
+        pa = [dataclasses.replace(p) for p in b2.patches]
+        pb = [dataclasses.replace(p) for p in b2.patches]
+        for p_, geo in ((pa[-1], geo_a), (pb[-1], geo_b)):
+            p_.geometry, p_.smoothen = geo, False
+            p_.x_centroid, p_.y_centroid, p_.radius, p_.length_x, p_.length_y = 0.5, 0.5, 0.2, 0.4, 0.3
+        ca, cb_ = dataclasses.replace(b2, patches=pa), dataclasses.replace(b2, patches=pb)
+        grid = pre_process.generate_grid(ca)
+        qa, qb = pre_process.generate_initial_condition(ca, grid), pre_process.generate_initial_condition(cb_, grid)
+        if geo_a == 6:
+            # (geometry 2 would also repaint the cells of its smooth_patch_id, m_create_patches.fpp:131-137;
+            # the vortex patch has no such clause) inside the circle: this patch; outside: the background
+            x = (grid[0][1:] + grid[0][:-1]) / 2
+            ins = ((x[None, :] - 0.5) ** 2 + (x[:, None] - 0.5) ** 2) <= 0.2 ** 2
+            assert ins.any() and not ins.all()
+            assert np.all(qa[0, 0][ins] == pa[-1].alpha_rho[0]) and np.all(qa[0, 0][~ins] == pa[0].alpha_rho[0])
+        else:
+            assert np.array_equal(qa[:4], qb[:4]) and np.array_equal(qa[5:], qb[5:])
+            assert (qa[4] >= qb[4]).all() and (qa[4] > qb[4]).any()
