@@ -79,7 +79,19 @@ def step_flops_per_cell(E: int, nd: int) -> int:
     return 3 * per_rhs
 
 
-def workload_case(name: str, n_gpus: int, cells: int | None, strong: bool = False):
+def stretch_grid(d: dict, nd: int) -> dict:
+    """Cluster the cells towards the middle of the domain with the reference's tanh-type stretching
+    (src/pre_process/m_grid.f90:171-187, a = 2: widths vary by ~2-3x): the sweeps then read per-cell
+    WENO coefficient tables (m_weno.fpp:168-363) instead of the uniform-grid constants."""
+    out = dict(d)
+    for ax in "xyz"[:nd]:
+        lo, hi = d[f'{ax}_domain%beg'], d[f'{ax}_domain%end']
+        out.update({f'stretch_{ax}': 'T', f'a_{ax}': 2.0, f'{ax}_a': lo + 0.3 * (hi - lo), f'{ax}_b': lo + 0.7 * (hi - lo), f'loops_{ax}': 1})
+    out['dt'] = d['dt'] * 0.25
+    return out
+
+
+def workload_case(name: str, n_gpus: int, cells: int | None, strong: bool = False, stretched: bool = False):
     """weak scaling: `cells` per GPU and direction, the global grid grows with the topology;
     strong scaling: ONE global grid of `cells` per direction, split by the reference's rule
     (m_mpi_proxy.fpp:163-203; 4096^2 on 8 ranks -> 4 x 2 blocks of 1024 x 2048)."""
@@ -115,6 +127,11 @@ def workload_case(name: str, n_gpus: int, cells: int | None, strong: bool = Fals
                 "(BASELINE configs[3]: 8192x4096 on 8 GPUs)")
     else:
         raise SystemExit(f"unknown workload {name}")
+    if stretched:
+        if name != "shockbubble_3d_512":
+            raise SystemExit("--stretched is wired for the default 3-D workload")
+        d = stretch_grid(d, 3)
+        desc += ", STRETCHED grid (per-cell WENO coefficient tables)"
     if strong:
         desc = desc.replace("cells per GPU", "cells in total (one grid, strong-scaled)")
     if name == "sod_1d_400":
@@ -276,6 +293,7 @@ def main():
     ap.add_argument("--cpu-sample-cells", type=int, default=None)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --cells per GPU (default); strong: one global grid of --cells per direction over all GPUs")
+    ap.add_argument("--stretched", action="store_true", help="stretch the grid (m_grid.f90:171-187): per-cell WENO coefficient tables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -288,7 +306,7 @@ def main():
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
     K, W = args.steps, max(args.warmup, 0)
     strong = args.scaling == "strong"
-    cfg, desc, topo = workload_case(args.workload, args.gpus, args.cells, strong)
+    cfg, desc, topo = workload_case(args.workload, args.gpus, args.cells, strong, args.stretched)
     nd, E = cfg.num_dims, cfg.sys_size
     ncell_total = int(np.prod(cfg.shape_glb))
     if strong:

@@ -64,6 +64,7 @@ struct SweepArgs {
     double Res[2][kMaxFluids];
     double iRes[2][kMaxFluids];  // 1/Res (fast build: the face stores 1/Re_avg, no divisions)
     int Re_idx[2][kMaxFluids], Re_size[2];
+    double iRe_f[2][kMaxFluids]; // 1/Re(i) of every FLUID, 0 where that fluid has none (in-sweep viscous path)
 };
 
 // viscous source flux + its RHS contribution for one direction (m_riemann_solvers.fpp:683-902,

@@ -401,17 +401,16 @@ template <int NF, int ND, int ID>
 __device__ __forceinline__ void visc_flux_fd(const SweepArgs &a, const double *L, const double *R, const double *vs,
                                              const double *dn, const double *ct, double *F) {
     constexpr int MOM = NF, EN = NF + ND, ADV = NF + ND + 1, O = ND > 1 ? 1 - ID : 0;
-    double iRe[2];                                     // 1/Re_avg = (1/Re_L + 1/Re_R)/2, :169-200, :225-230
+    // 1/Re_avg = (1/Re_L + 1/Re_R)/2 with 1/Re_K = max(sum_f alpha_K(f)/Re(f), sgm_eps), :169-200, :225-230;
+    // iRe_f holds 1/Re per FLUID (0 for the fluids without that viscosity): no index lists, no branches
+    double iRe[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        double rl = a.Re_size[i] > 0 ? 0.0 : -1e6, rr = rl;
-        for (int q = 0; q < a.Re_size[i]; q++) {
-            double al = L[ADV], ar = R[ADV];
+        double rl = L[ADV]*a.iRe_f[i][0], rr = R[ADV]*a.iRe_f[i][0];
 #pragma unroll
-            for (int f = 1; f < NF; f++)
-                if (a.Re_idx[i][q] == f) { al = L[ADV + f]; ar = R[ADV + f]; }
-            rl = fma(al, a.iRes[i][q], rl);
-            rr = fma(ar, a.iRes[i][q], rr);
+        for (int f = 1; f < NF; f++) {
+            rl = fma(L[ADV + f], a.iRe_f[i][f], rl);
+            rr = fma(R[ADV + f], a.iRe_f[i][f], rr);
         }
         iRe[i] = 0.5*(fmax(rl, 1e-16) + fmax(rr, 1e-16));
     }
@@ -841,7 +840,7 @@ __device__ __forceinline__ void prim_regs(double (&q)[2*NF + ND + 1], const doub
 }
 
 template <int NF, int ND, int COEF, bool BC4, int VISC, int WO>
-__global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(32*kWarpsX, (COEF == 1 && WO == 5 && !MFC_STRICT) ? 3 : kCtasX) k_xstream(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = kRingX, SLOT = slot_doubles(E, kWX);
     constexpr int PR = kPrimRing, XR = kXchRing;
     constexpr bool ACC = false, RK = ND == 1;          // x is the first direction, and the last one in 1-D
@@ -1075,7 +1074,7 @@ __global__ void __launch_bounds__(32*kWarpsX, kCtasX) k_xstream(const __grid_con
 // before a slot is handed back.  Lanes beyond the domain compute on zero-filled columns.
 // ------------------------------------------------------------------------------------------
 template <int NF, int ND, int DIR, int COEF, bool BC4, int VISC, int WO>
-__global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRICT) ? 2 : march_ctas(DIR, ND)) k_march3(const __grid_constant__ SweepArgs a) {
     constexpr int E = 2*NF + ND + 1, ADV = NF + ND + 1, R = march_ring(DIR, ND), SLOT = slot_doubles(E, kWY);
     constexpr bool ACC = true, RK = DIR == ND - 1;
     constexpr int NS = march_slots(DIR, ND);           // slots per warp: ring | rin | qin (RK) | outs
@@ -1143,14 +1142,17 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
     // plane-relative element offset of cell s-1 of my column (lanes beyond the domain: column N)
     unsigned off = (unsigned)(base + (min(j0 + lane, g.N[0]) - j0) + (long long)(s0 - 3)*ss);
     Weno<COEF, WO> weno;
-    // carried from cell s-1 / face s-3/2: right-face state, flux, face velocity
-    double vRp[E], Fp[E], ufp = 0.0;
+    // carried from cell s-1 / face s-3/2: right-face state, flux, face velocity.  Two sets that swap
+    // roles every iteration (the loop below is unrolled by two), so that the hand-over from one cell to
+    // the next is a renaming, not 2E+1 register moves.
+    struct Carry { double vR[E], F[E], uf; };
+    Carry cA, cB;
 #pragma unroll
-    for (int v = 0; v < E; v++) { vRp[v] = 0.0; Fp[v] = 0.0; }
+    for (int v = 0; v < E; v++) { cA.vR[v] = 0.0; cA.F[v] = 0.0; }
+    cA.uf = 0.0;
     // One iteration of the march: reconstruct cell s, solve face s-1/2 against the carried
     // right-face state of cell s-1, finish cell s-1 with the carried flux of face s-3/2.
-#pragma unroll 1
-    for (int s = s0 - 1; s <= s1 + 1; s++) {
+    auto iter = [&](const int s, const Carry &P, Carry &Nx) {
         mbar_wait(&bar[slot_cv], phase_cv);            // row s+2 (AHEAD: s+3) has arrived
         double *const row_cv = ring + slot_cv*SLOT + lane;
         if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
@@ -1167,18 +1169,47 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
                 vg_l[v] = __ldg(pl); vg_r[v] = __ldg(pl + uss);
             }
         }
-        double vL[E], vRn[E];
+        double vL[E];
 #pragma unroll
         for (int v = 0; v < E; v++) {
             const double st[5] = {p0[v*kWY], p1[v*kWY], p2[v*kWY], p3[v*kWY], p4[v*kWY]};
-            weno(st, vL[v], vRn[v]);
+            weno(st, vL[v], Nx.vR[v]);
         }
         const bool fin = s >= s0 + 1;                  // cell s-1 is finished in this iteration
         {   // face s-1/2.  The warm-up iteration s0-1 solves it too (against the zero state; the
             // result is overwritten before any use): one straight-line body, no second copy
-            double Fn[E], ufn;
-            CellIn<E, ACC, RK> in;
-            if (fin) {                                 // operand rows requested one iteration ago
+            double Ls[BC4 ? E : 1];
+            if (BC4) {
+#pragma unroll
+                for (int v = 0; v < E; v++) Ls[v] = P.vR[v];
+                if (a.bc_beg == -4 && s == 0) {
+#pragma unroll
+                    for (int v = 0; v < E; v++) Ls[v] = vL[v];
+                }
+                if (a.bc_end == -4 && s == g.N[DIR] + 1) {
+#pragma unroll
+                    for (int v = 0; v < E; v++) vL[v] = Ls[v];
+                }
+            }
+            const double *L = BC4 ? Ls : P.vR;
+            double vs[ND];
+            if (AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
+            hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Nx.F, Nx.uf, vs);
+            if (VISC == 1 && on && s >= s0) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
+            if (VISC == 2) {                           // viscous source flux of face s-1/2, folded into Fn
+                double dn[ND], ct[ND];
+                const double rd = __ldg(a.rdcc + s - 1 + g.b);       // 1/(s_cc(s) - s_cc(s-1))
+#pragma unroll
+                for (int v = 0; v < ND; v++) {
+                    dn[v] = (p2[(NF + v)*kWY] - p1[(NF + v)*kWY])*rd;   // rows s, s-1
+                    ct[v] = 0.5*(vg_l[v] + vg_r[v]);
+                }
+                visc_flux_fd<NF, ND, DIR>(a, L, vL, vs, dn, ct, Nx.F);
+            }
+            if (fin) {
+                // operand rows (requested one iteration ago), read only now: 2E doubles that need not be
+                // live across the Riemann solve
+                CellIn<E, ACC, RK> in;
                 mbar_wait(bar_r, phase_op);
 #pragma unroll
                 for (int v = 0; v < E; v++) in.r[v] = rin[v*kWY + lane];
@@ -1195,46 +1226,13 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
 #endif
                 }
                 phase_op ^= 1u;
-            }
-            double Ls[BC4 ? E : 1];
-            if (BC4) {
-#pragma unroll
-                for (int v = 0; v < E; v++) Ls[v] = vRp[v];
-                if (a.bc_beg == -4 && s == 0) {
-#pragma unroll
-                    for (int v = 0; v < E; v++) Ls[v] = vL[v];
-                }
-                if (a.bc_end == -4 && s == g.N[DIR] + 1) {
-#pragma unroll
-                    for (int v = 0; v < E; v++) vL[v] = Ls[v];
-                }
-            }
-            const double *L = BC4 ? Ls : vRp;
-            double vs[ND];
-            if (AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
-            hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Fn, ufn, vs);
-            if (VISC == 1 && on && s >= s0) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
-            if (VISC == 2) {                           // viscous source flux of face s-1/2, folded into Fn
-                double dn[ND], ct[ND];
-                const double rd = __ldg(a.rdcc + s - 1 + g.b);       // 1/(s_cc(s) - s_cc(s-1))
-#pragma unroll
-                for (int v = 0; v < ND; v++) {
-                    dn[v] = (p2[(NF + v)*kWY] - p1[(NF + v)*kWY])*rd;   // rows s, s-1
-                    ct[v] = 0.5*(vg_l[v] + vg_r[v]);
-                }
-                visc_flux_fd<NF, ND, DIR>(a, L, vL, vs, dn, ct, Fn);
-            }
-            if (fin) {
                 double y[E];
-                finish_vals<NF, ND, kWY, ACC, RK>(a, a.rds[s - 1 + g.b], p1, in, Fp, ufp, Fn, ufn, y);   // p1: row s-1
+                finish_vals<NF, ND, kWY, ACC, RK>(a, a.rds[s - 1 + g.b], p1, in, P.F, P.uf, Nx.F, Nx.uf, y);   // p1: row s-1
                 if (lane == 0) tma_store_wait_read();  // the previous row has left the output slot
                 __syncwarp();
 #pragma unroll
                 for (int v = 0; v < E; v++) outs[v*kWY + lane] = y[v];
             }
-#pragma unroll
-            for (int v = 0; v < E; v++) Fp[v] = Fn[v];
-            ufp = ufn;
         }
         // One proxy fence per iteration orders, for the whole warp, (a) the output row written
         // above before the bulk store reads it, (b) the reads of the operand slots and of ring
@@ -1260,8 +1258,11 @@ __global__ void __launch_bounds__(32*kWarpsY, march_ctas(DIR, ND)) k_march3(cons
         p0 = p1; p1 = p2; p2 = p3; p3 = p4;
         p4 += SLOT;
         if (p4 >= ring_end) p4 -= R*SLOT;
-#pragma unroll
-        for (int v = 0; v < E; v++) vRp[v] = vRn[v];
+    };
+#pragma unroll 1
+    for (int s = s0 - 1; s <= s1 + 1; s += 2) {
+        iter(s, cA, cB);
+        if (s + 1 <= s1 + 1) iter(s + 1, cB, cA);
     }
     if (lane == 0) tma_store_wait_read();              // the output slot must outlive the last store's read
 }

@@ -422,6 +422,8 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
                 a.iRes[i][k] = k < S.Re_size[i] ? 1.0/S.Res[i][k] : 0.0;
             }
         }
+        for (int i = 0; i < 2; i++)
+            for (int k = 0; k < kMaxFluids; k++) a.iRe_f[i][k] = (k < S.nf && S.p.Re[k][i] > 0.0) ? 1.0/S.p.Re[k][i] : 0.0;
         a.coef_uniform = S.coef_uniform[d]; a.weno_order = S.p.weno_order;
         a.stab_out = (fuse_stab && d == 0) ? S.stab_dev : nullptr;
         a.rds_t[0] = S.rds[1]; a.rds_t[1] = S.rds[2];

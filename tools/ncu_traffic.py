@@ -19,8 +19,8 @@ kern = {}
 seen = {}
 for d in data:
     name = d[ik]
-    if "k_xrow" in name:
-        label = "k_xrow"
+    if "k_xstream" in name:
+        label = "k_xstream"
     elif "k_march3" in name:
         dirs = name.split("k_march3<")[1].split(",")
         label = "k_march3<%s>" % ("y" if dirs[2].strip().endswith("1") else "z")
