@@ -34,6 +34,10 @@ struct SweepArgs {
     // halo is still in flight) = 1: the cells that read no x ghost column, 2: the two boundary
     // strips, 0: everything in one launch
     int xsplit, xs_ntx, xs_lo, xs_hi, xs_strip, xs_items;
+    // rows / planes this x launch covers (multi-rank runs sweep x piece by piece as the x halo arrives,
+    // viscous runs sweep the rows that need no y ghosts while the y halo is in flight): rows
+    // xs_k0 .. xs_k0 + xs_nk - 1 of planes xs_z0 .. xs_z0 + xs_nz - 1; xs_nk = 0 means everything
+    int xs_k0, xs_nk, xs_z0, xs_nz;
     // fused stability criterion (x kernel of stage 1, inviscid fast build): ICFL max of the
     // cells this kernel finishes, m_data_output.fpp:215-233; nullptr = off
     unsigned long long *stab_out;
@@ -92,6 +96,7 @@ struct ViscArgs {
     const double *q1, *qs;
     double *qout;
     double dt;
+    int k_lo, k_hi;            // k_vgrad: cell rows k_lo .. k_hi (within -1 .. N+1)
 };
 
 struct BcArgs {
@@ -104,8 +109,9 @@ struct BcArgs {
 struct HaloArgs {
     GridDesc g;
     double *q;
-    double *buf;
+    double *buf;           // the piece's own contiguous message: E runs of cnt doubles
     int dir, side, E;      // pack: side 0 = first b interior layers, 1 = last b;  unpack: ghosts at beg / end
+    long long idx0, cnt;   // the piece: slab elements idx0 .. idx0 + cnt - 1 of every variable (cnt = 0: the whole slab)
 };
 
 struct PrimArgs {

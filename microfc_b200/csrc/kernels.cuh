@@ -866,8 +866,8 @@ __global__ void __launch_bounds__(32*kWarpsX, (COEF == 1 && WO == 5 && !MFC_STRI
         ja = a.xs_lo + (int)(tix*W/a.xs_ntx);
         jb = a.xs_lo + (int)((tix + 1)*W/a.xs_ntx) - 1;
     }
-    const int k0 = rb*a.rows, l = blockIdx.z;
-    const int nr = min(a.rows, g.N[1] + 1 - k0);
+    const int k0 = a.xs_k0 + rb*a.rows, l = (int)blockIdx.z + a.xs_z0;
+    const int nr = min(a.rows, a.xs_k0 + a.xs_nk - k0);
     const int Lt = jb - ja + 7;                        // entries of a row that exist: cells ja-3 .. jb+3
     const int Ls = max(Lt, 32);                        // a chunk touches at most two rows
     const int nload = (nr*Ls + 31) >> 5;               // chunks that bring new cells
@@ -1357,27 +1357,27 @@ __global__ void __launch_bounds__(256) k_bc(const __grid_constant__ BcArgs a) {
 // sides stream along x.
 __global__ void __launch_bounds__(256) k_halo_pack(const __grid_constant__ HaloArgs a) {
     const GridDesc &g = a.g;
-    const long long n = slab_count(g, a.dir);
-    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    const long long loc = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (loc >= a.cnt) return;
+    const long long idx = a.idx0 + loc;
     const int v = blockIdx.y;
     int t0, t1, layer;
     bc_decode(g, a.dir, idx, t0, t1, layer);
     const int N = g.N[a.dir];
     const int src = a.side == 0 ? layer : N - g.b + 1 + layer;     // first b / last b interior layers
-    a.buf[(long long)v*n + idx] = a.q[(long long)v*g.fstride + bc_cell(g, a.dir, src, t0, t1)];
+    a.buf[(long long)v*a.cnt + loc] = a.q[(long long)v*g.fstride + bc_cell(g, a.dir, src, t0, t1)];
 }
 __global__ void __launch_bounds__(256) k_halo_unpack(const __grid_constant__ HaloArgs a) {
     const GridDesc &g = a.g;
-    const long long n = slab_count(g, a.dir);
-    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    const long long loc = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (loc >= a.cnt) return;
+    const long long idx = a.idx0 + loc;
     const int v = blockIdx.y;
     int t0, t1, layer;
     bc_decode(g, a.dir, idx, t0, t1, layer);
     const int N = g.N[a.dir];
     const int dst = a.side == 0 ? -g.b + layer : N + 1 + layer;    // ghost layers in ascending order
-    a.q[(long long)v*g.fstride + bc_cell(g, a.dir, dst, t0, t1)] = a.buf[(long long)v*n + idx];
+    a.q[(long long)v*g.fstride + bc_cell(g, a.dir, dst, t0, t1)] = a.buf[(long long)v*a.cnt + loc];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1475,7 +1475,7 @@ template <int NF, int ND>
 __global__ void __launch_bounds__(128) k_vgrad(const __grid_constant__ ViscArgs a) {
     const GridDesc &g = a.g;
     const int j = (int)(blockIdx.y*blockDim.x + threadIdx.x) - 1;
-    const int k = ND > 1 ? (int)blockIdx.x - 1 : 0;
+    const int k = ND > 1 ? (int)blockIdx.x + a.k_lo : 0;
     if (j > g.N[0] + 1) return;
     const int c[3] = {j, k, 0};
     const long long cell = g.at(j, k, 0), fs = g.fstride;

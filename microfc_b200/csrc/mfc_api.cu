@@ -73,6 +73,18 @@ struct Sim {
     cudaEvent_t ev_q = nullptr, ev_halo[3] = {nullptr, nullptr, nullptr};
     bool halo_pending[3] = {false, false, false};
     bool overlap = false, xsplit_on = false;
+    // the x halo travels in xpieces consecutive pieces (plane ranges in 3-D, row ranges in 2-D), each
+    // with its own event, and the x sweep follows piece by piece: only the first piece is exposed
+    static constexpr int kMaxPieces = 8;
+    int xpieces = 1;
+    cudaEvent_t ev_xp[kMaxPieces] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // pieces 1.. of the x sweep run on streams of their own, so that the tail of one piece is backfilled by
+    // the CTAs of the next (on one stream every piece would drain before the next starts)
+    cudaStream_t xstream[kMaxPieces] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_xdone[kMaxPieces] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_pre = nullptr;
+    bool xp_pending = false;
+    bool visc_overlap = false;         // viscous fused path: y halo in flight under the x sweep of the inner rows
     double *state[3] = {nullptr, nullptr, nullptr};
     int cur = 0;                       // which buffer holds q_cons_ts(1)
     const double *last_q = nullptr;    // state of the most recent RHS evaluation (what q_prim_vf reflects)
@@ -176,6 +188,10 @@ void free_all() {
     if (S.comm && S.nccl.CommDestroy) { S.nccl.CommDestroy(S.comm); S.comm = nullptr; }
     if (S.ev_q) { cudaEventDestroy(S.ev_q); S.ev_q = nullptr; }
     for (auto &e : S.ev_halo) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto &e : S.ev_xp) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto &e : S.ev_xdone) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto &x : S.xstream) if (x) { cudaStreamDestroy(x); x = nullptr; }
+    if (S.ev_pre) { cudaEventDestroy(S.ev_pre); S.ev_pre = nullptr; }
     if (S.cs) { cudaStreamDestroy(S.cs); S.cs = nullptr; }
     S.overlap = false;
     if (S.st) { cudaStreamDestroy(S.st); S.st = nullptr; }
@@ -230,28 +246,44 @@ const TensorMap *state_tmap(const double *q, int which) {
 // ---- ghost cells: physical BCs (k_bc) and processor boundaries (pack / NCCL / unpack) --------
 // processor boundaries of direction d: pack, ncclSend/ncclRecv with the +-d neighbours, unpack
 // (m_mpi_proxy.fpp:468-979), all on stream st
-int exchange_dir(double *q, int d, cudaStream_t st) {
+int exchange_dir(double *q, int d, cudaStream_t st, long long idx0 = 0, long long cnt = 0) {
     if (!S.comm) return fail(MFC_B200_ESTATE, "processor boundary present but mfc_b200_comm_init was not called");
-    const long long n = slab_count(S.g, d)*S.E;
+    if (cnt <= 0) { idx0 = 0; cnt = slab_count(S.g, d); }
+    const long long n = cnt*S.E;                         // doubles per message; piece p lives at E*idx0 of the buffers
     for (int s = 0; s < 2; s++) {
         if (S.bc[d][s] < 0) continue;
-        HaloArgs h{S.g, q, S.sendbuf[d][s], d, s, S.E};
+        HaloArgs h{S.g, q, S.sendbuf[d][s] + S.E*idx0, d, s, S.E, idx0, cnt};
         Scope sc(KC_PACK, st); sc.done(S.L->halo_pack(h, st));
     }
     // sends: [to beg: my first layers] [to end: my last layers];  receives in the opposite
     // order so that two exchanges with the SAME peer (2 ranks, periodic) pair up correctly.
     NK(S.nccl.GroupStart());
     for (int s = 0; s < 2; s++)
-        if (S.bc[d][s] >= 0) NK(S.nccl.Send(S.sendbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, st));
+        if (S.bc[d][s] >= 0) NK(S.nccl.Send(S.sendbuf[d][s] + S.E*idx0, (size_t)n, ncclDouble, S.bc[d][s], S.comm, st));
     for (int s = 1; s >= 0; s--)
-        if (S.bc[d][s] >= 0) NK(S.nccl.Recv(S.recvbuf[d][s], (size_t)n, ncclDouble, S.bc[d][s], S.comm, st));
+        if (S.bc[d][s] >= 0) NK(S.nccl.Recv(S.recvbuf[d][s] + S.E*idx0, (size_t)n, ncclDouble, S.bc[d][s], S.comm, st));
     NK(S.nccl.GroupEnd());
     for (int s = 0; s < 2; s++) {
         if (S.bc[d][s] < 0) continue;
-        HaloArgs h{S.g, q, S.recvbuf[d][s], d, s, S.E};
+        HaloArgs h{S.g, q, S.recvbuf[d][s] + S.E*idx0, d, s, S.E, idx0, cnt};
         Scope sc(KC_UNPACK, st); sc.done(S.L->halo_unpack(h, st));
     }
     return 0;
+}
+// piece p of the x slab: a range of planes (3-D) or rows (2-D); the slab index runs layer fastest,
+// then row, then plane (bc_decode), so a piece is a contiguous index range
+void xpiece_range(int p, int &k0, int &nk, int &z0, int &nz, long long &idx0, long long &cnt) {
+    const GridDesc &g = S.g;
+    const int ny = g.N[1] + 1, nzz = g.N[2] + 1, P = S.xpieces;
+    if (S.nd == 3) {
+        z0 = (int)((long long)nzz*p/P); nz = (int)((long long)nzz*(p + 1)/P) - z0;
+        k0 = 0; nk = ny;
+        idx0 = (long long)g.b*ny*z0; cnt = (long long)g.b*ny*nz;
+    } else {
+        k0 = (int)((long long)ny*p/P); nk = (int)((long long)ny*(p + 1)/P) - k0;
+        z0 = 0; nz = 1;
+        idx0 = (long long)g.b*k0; cnt = (long long)g.b*nk;
+    }
 }
 int physical_bc_dir(double *q, int d) {
     if (S.bc[d][0] >= 0 && S.bc[d][1] >= 0) return 0;
@@ -280,10 +312,19 @@ int ghosts_begin(double *q) {
     }
     CK(cudaEventRecord(S.ev_q, S.st));
     CK(cudaStreamWaitEvent(S.cs, S.ev_q, 0));
+    S.xp_pending = false;
     for (int d = 0; d < S.nd; d++) {
         if (S.bc[d][0] < 0 && S.bc[d][1] < 0) continue;
         int rc;
-        if ((rc = exchange_dir(q, d, S.cs))) return rc;
+        if (d == 0 && S.xpieces > 1 && !S.xsplit_on) {
+            for (int p = 0; p < S.xpieces; p++) {
+                int k0, nk, z0, nz; long long idx0, cnt;
+                xpiece_range(p, k0, nk, z0, nz, idx0, cnt);
+                if ((rc = exchange_dir(q, 0, S.cs, idx0, cnt))) return rc;
+                CK(cudaEventRecord(S.ev_xp[p], S.cs));
+            }
+            S.xp_pending = true;
+        } else if ((rc = exchange_dir(q, d, S.cs))) return rc;
         CK(cudaEventRecord(S.ev_halo[d], S.cs));
         S.halo_pending[d] = true;
     }
@@ -373,7 +414,19 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         if ((rc = run_stability(S.last_q, dt))) return rc;
     // m_rhs.fpp:435.  Anything that reads the whole ghosted box needs every direction complete.
     const bool need_all = stop || S.viscous;
-    if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
+    // viscous, in-sweep path, y neighbours: x ghosts first (whole, on the compute stream), then the y
+    // exchange -- whose messages span the x ghosts and so carry the corners, m_mpi_proxy.fpp:736-739 --
+    // goes to the communication stream and flies under k_vgrad / the x sweep of rows 1 .. n-1, which
+    // read no y ghost; rows 0 and n and the y sweep follow its arrival
+    const bool vo = S.visc_overlap && !stop && S.nd == 2 && (S.bc[1][0] >= 0 || S.bc[1][1] >= 0) && S.g.N[1] >= 8;
+    if (vo) {
+        if ((S.bc[0][0] >= 0 || S.bc[0][1] >= 0) && (rc = exchange_dir(q, 0, S.st))) return rc;
+        if ((rc = physical_bc_dir(q, 0))) return rc;
+        CK(cudaEventRecord(S.ev_q, S.st));
+        CK(cudaStreamWaitEvent(S.cs, S.ev_q, 0));
+        if ((rc = exchange_dir(q, 1, S.cs))) return rc;
+        CK(cudaEventRecord(S.ev_halo[1], S.cs));
+    } else if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
     // :445-447 (fused into the sweeps; the viscous kernels read the velocity planes -- the in-sweep
     // viscous path only needs them for the cross-direction gradients, i.e. not in 1-D)
     if (S.viscous && (!S.visc_fused || stop) && (rc = run_prim(q))) return rc;
@@ -401,7 +454,10 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         va.eps = S.p.weno_eps; va.nf = S.nf; va.weno_Re_flux = S.p.weno_Re_flux;
         va.Re_size[0] = S.Re_size[0]; va.Re_size[1] = S.Re_size[1];
         if (S.p.weno_Re_flux) { Scope sc(KC_VISC); sc.done(S.L->visc_grad(S.nd, va, S.st)); }
-        if (S.visc_fused && S.nd > 1) { Scope sc(KC_VISC); sc.done(S.L->vgrad(S.nd, va, S.st)); }
+        if (S.visc_fused && S.nd > 1) {
+            va.k_lo = vo ? 1 : -1; va.k_hi = vo ? S.g.N[1] - 1 : S.g.N[1] + 1;
+            Scope sc(KC_VISC); sc.done(S.L->vgrad(S.nd, va, S.st));
+        }
     }
     for (int d = 0; d < S.nd; d++) {                         // :469
         SweepArgs a{};
@@ -432,7 +488,8 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         // (optional, MFC_B200_XSPLIT=1: the two boundary strips cost 2 x 32 lane slots per row whatever
         // their width, ~12 % of a 512-cell row, against ~0.2 ms of exposed x exchange at 512^3)
         const bool split_x = d == 0 && S.overlap && S.xsplit_on && S.halo_pending[0] && S.nd >= 2;
-        if (!split_x && (rc = ghosts_ready(q, d))) return rc;
+        const bool pieces_x = d == 0 && (S.xp_pending || vo);
+        if (!split_x && !pieces_x && !(vo && d == 1) && (rc = ghosts_ready(q, d))) return rc;
         {
             const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
             if (!tq || !t1) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
@@ -444,7 +501,42 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         }
         Scope sc(KC_SWEEP_X + d);
         int n = 0;
-        if (split_x) {
+        if (d == 0 && vo) {
+            // rows 1 .. n-1 now; then, with the y halo in place: the gradients of rows -1, 0, n, n+1 and
+            // the x sweep of rows 0 and n
+            a.xs_k0 = 1; a.xs_nk = S.g.N[1] - 1; a.xs_z0 = 0; a.xs_nz = 1;
+            n = S.L->sweep(S.nf, S.nd, 0, a, S.st);
+            if (!n) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
+            CK(cudaStreamWaitEvent(S.st, S.ev_halo[1], 0));
+            if ((rc = physical_bc_dir(q, 1))) return rc;
+            for (int side = 0; side < 2; side++) {
+                va.k_lo = side == 0 ? -1 : S.g.N[1]; va.k_hi = va.k_lo + 1;
+                S.launches += S.L->vgrad(S.nd, va, S.st);
+            }
+            for (int side = 0; side < 2; side++) {
+                a.xs_k0 = side == 0 ? 0 : S.g.N[1]; a.xs_nk = 1;
+                n += S.L->sweep(S.nf, S.nd, 0, a, S.st);
+            }
+            a.xs_nk = 0;
+        } else if (d == 0 && S.xp_pending) {
+            // the x halo arrives piece by piece (ghosts_begin): sweep each piece as soon as it is there
+            if ((rc = physical_bc_dir(q, 0))) return rc;
+            CK(cudaEventRecord(S.ev_pre, S.st));
+            for (int p = 0; p < S.xpieces; p++) {
+                long long idx0, cnt;
+                xpiece_range(p, a.xs_k0, a.xs_nk, a.xs_z0, a.xs_nz, idx0, cnt);
+                cudaStream_t xs = p == 0 ? S.st : S.xstream[p];
+                if (p > 0) CK(cudaStreamWaitEvent(xs, S.ev_pre, 0));
+                CK(cudaStreamWaitEvent(xs, S.ev_xp[p], 0));
+                const int np = S.L->sweep(S.nf, S.nd, 0, a, xs);
+                if (!np) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
+                n += np;
+                if (p > 0) CK(cudaEventRecord(S.ev_xdone[p], xs));
+            }
+            for (int p = 1; p < S.xpieces; p++) CK(cudaStreamWaitEvent(S.st, S.ev_xdone[p], 0));
+            a.xs_nk = 0;
+            S.xp_pending = false; S.halo_pending[0] = false;
+        } else if (split_x) {
             a.xsplit = 1;
             const int n1 = S.L->sweep(S.nf, S.nd, d, a, S.st);
             if (!n1) return fail(MFC_B200_EUNSUPPORTED, "no sweep kernel instantiated for this (num_fluids, num_dims)");
@@ -751,6 +843,20 @@ int mfc_b200_comm_init(const unsigned char id[128], int rank, int nranks) {
         S.overlap = !S.viscous && !(e && e[0] == '0');
         const char *x = std::getenv("MFC_B200_XSPLIT");
         S.xsplit_on = x && x[0] == '1';
+        for (auto &ev : S.ev_xp) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto &ev : S.ev_xdone) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S.ev_pre, cudaEventDisableTiming));
+        for (auto &x : S.xstream) CK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        // x halo pieces of >= 24 MB per message (smaller ones are latency-bound and gain nothing; measured at
+        // 512^3, 67 MB per face: 2 pieces 53.95 ms/step, 4 pieces 54.16, 8 pieces 54.21, unpieced 55.10)
+        const long long bytes = slab_count(S.g, 0)*S.E*(long long)sizeof(double);
+        const char *pc = std::getenv("MFC_B200_XPIECES");
+        long long P = pc ? std::atoll(pc) : bytes/(24LL << 20);
+        const int lim = S.nd == 3 ? S.g.N[2] + 1 : S.g.N[1] + 1;
+        if (P > Sim::kMaxPieces) P = Sim::kMaxPieces;
+        if (P > lim/8) P = lim/8;
+        S.xpieces = (S.nd >= 2 && S.overlap && P >= 2) ? (int)P : 1;
+        S.visc_overlap = S.visc_fused && !(e && e[0] == '0');
     }
     return 0;
 }

@@ -45,6 +45,8 @@ CASES = {
     # pack / unpack index maps and neighbour tables
     "advection_2d_ysplit": (lambda: _advection_64x256(), 20),                                 # 2 ranks: 1 x 2
     "viscous_wave_2d_ysplit": (lambda: (cases.viscous_wave_2d(N=128, Nx=64, weno_Re_flux=True), cases.viscous_wave_state), 10),   # 1 x 2, periodic y, corners
+    # in-sweep viscous path with y neighbours: the y halo flies under the x sweep of the inner rows
+    "viscous_wave_2d_fd_ysplit": (lambda: (cases.viscous_wave_2d(N=128, Nx=64, weno_Re_flux=False), cases.viscous_wave_state), 10),
     "shockbubble_3d_ysplit": (lambda: cases.shockbubble_3d(ncx=26, ncy=52, ncz=26), 6),      # 2 ranks: 1 x 2 x 1
     "shockbubble_3d_zsplit": (lambda: cases.shockbubble_3d(ncx=26, ncy=26, ncz=52), 6),      # 2 ranks: 1 x 1 x 2
     "shockbubble_3d_zsplit_periodic": (lambda: cases.shockbubble_3d(ncx=26, ncy=26, ncz=52, periodic_z=True), 6),
@@ -85,6 +87,9 @@ def main():
         # the split x launch (interior cells while the x halo is in flight, then the boundary strips)
         # is off by default; the wide cases switch it on
         os.environ["MFC_B200_XSPLIT"] = "1" if "wide" in name else "0"
+        # the x halo travels in pieces only above 16 MB per face: force three pieces here so that the
+        # piecewise exchange + piecewise x sweep are what these small cases run
+        os.environ["MFC_B200_XPIECES"] = "3"
         for strict in (True, False):
             sim = Simulation(cfg, cb, rank=rank, num_procs=world, strict=strict, device=local, broadcast_id=bcast)
             sim.upload(sim.scatter(q0))

@@ -32,7 +32,7 @@ def _free_port():
     (2, ["sod_1d", "shockbubble_2d", "shearlayer_2d", "shockdroplet_2d", "shockbubble_3d", "viscous_2d", "shockdroplet_2d_viscous",
          "shockbubble_2d_wide", "shockbubble_3d_wide", "viscous_wave_2d_weno", "viscous_wave_2d_fd",
          # split along y / z by the reference's rule
-         "advection_2d_ysplit", "viscous_wave_2d_ysplit", "shockbubble_3d_ysplit", "shockbubble_3d_zsplit",
+         "advection_2d_ysplit", "viscous_wave_2d_ysplit", "viscous_wave_2d_fd_ysplit", "shockbubble_3d_ysplit", "shockbubble_3d_zsplit",
          "shockbubble_3d_zsplit_periodic"]),
     (4, ["shockbubble_2d", "shearlayer_2d", "shockbubble_3d", "viscous_2d", "shockdroplet_2d_viscous", "viscous_wave_2d_weno",
          "viscous_wave_2d_fd", "shockbubble_3d_yzsplit", "shockbubble_3d_xysplit"]),
