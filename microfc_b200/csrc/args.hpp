@@ -24,6 +24,10 @@ struct SweepArgs {
     double eps, dt;
     double gammas[kMaxFluids], pi_infs[kMaxFluids];
     int bc_beg, bc_end;    // boundary codes of this direction (Riemann-state extrapolation, -4)
+    // y / z march: effective code (-1, -2, <= -3) of a PHYSICAL boundary whose ghost rows the march
+    // synthesises by streaming the source row instead (no k_bc launch for this direction); 0 = read
+    // the ghost rows from memory
+    int map_beg, map_end;
     int first_dir;         // 1: RHS assigned (m_rhs.fpp:567-576), 0: accumulated (:610-620)
     int rk_mode;           // 0: store RHS; 1..4: fused update, see rk_apply()
     int seg;               // cells per thread along the sweep (march kernels)

@@ -1112,10 +1112,23 @@ __global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRI
     // tensor coordinates of row r of the warp's columns: (x, y, z) in the padded box for the
     // stage state; interior coordinates (cell indices) for the operand / output rows
     const int cx = j0 + kXoff, cy = (DIR == 1 ? 0 : t) + g.yoff, cz = (DIR == 1 ? t : 0) + g.zoff;
+    // Ghost rows of a PHYSICAL boundary of this direction are not read from memory: the row the
+    // boundary condition would have copied there (m_rhs.fpp:807-905: edge row for bc <= -3, mirror row
+    // for -2, wrapped row for -1) is streamed in its place, and for -2 the normal velocity changes sign
+    // after the conversion -- so k_bc is not launched for this direction at all (map_beg / map_end = the
+    // effective boundary code, 0 = the ghosts are real: processor boundary, or mapping switched off).
+    // source row of ghost row r: r < 0 -> lo_a + lo_b*r, r > N -> hi_a + hi_b*r (identity when not mapped)
+    const int Nd = g.N[DIR];
+    const int lo_a = a.map_beg == 0 ? 0 : (a.map_beg <= -3 ? 0 : (a.map_beg == -2 ? -1 : Nd + 1));
+    const int lo_b = a.map_beg == 0 ? 1 : (a.map_beg <= -3 ? 0 : (a.map_beg == -2 ? -1 : 1));
+    const int hi_a = a.map_end == 0 ? 0 : (a.map_end <= -3 ? Nd : (a.map_end == -2 ? 2*Nd + 1 : -Nd - 1));
+    const int hi_b = a.map_end == 0 ? 1 : (a.map_end <= -3 ? 0 : (a.map_end == -2 ? -1 : 1));
+    const bool mir_lo = a.map_beg == -2, mir_hi = a.map_end == -2;
     if (lane == 0) {
         for (int r = r_first; r < r_first + R && r <= r_last; r++) {
+            const int rs = r < 0 ? lo_a + lo_b*r : (r > Nd ? hi_a + hi_b*r : r);
             mbar_expect_tx(&bar[r - r_first], kRowBytes);
-            tma_load_row(ring + (r - r_first)*SLOT, &a.tm_q, cx, DIR == 1 ? cy + r : cy, DIR == 1 ? cz : cz + r, &bar[r - r_first]);
+            tma_load_row(ring + (r - r_first)*SLOT, &a.tm_q, cx, DIR == 1 ? cy + rs : cy, DIR == 1 ? cz : cz + rs, &bar[r - r_first]);
         }
         // operands of the first cell finished (s0): both rows complete the same barrier
         mbar_expect_tx(bar_r, need_q1 ? 2*kRowBytes : kRowBytes);
@@ -1133,6 +1146,10 @@ __global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRI
     for (int i = 0; i < 4 + (AHEAD ? 1 : 0); i++) {    // rows s0-3 .. s0 (+ s0+1)
         mbar_wait(&bar[slot_cv], phase_cv);
         prim_in_place<NF, ND, kWY>(ring + slot_cv*SLOT + lane, a.gammas, a.pi_infs);
+        if ((mir_lo && r_first + i < 0) || (mir_hi && r_first + i > Nd)) {   // mirrored ghost row: -u_normal
+            double *un = ring + slot_cv*SLOT + lane + (NF + DIR)*kWY;
+            *un = -*un;
+        }
         if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
     }
     const double *p0 = ring + lane, *p1 = p0 + SLOT, *p2 = p1 + SLOT, *p3 = p2 + SLOT, *p4 = p3 + SLOT;
@@ -1156,7 +1173,10 @@ __global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRI
         mbar_wait(&bar[slot_cv], phase_cv);            // row s+2 (AHEAD: s+3) has arrived
         double *const row_cv = ring + slot_cv*SLOT + lane;
         if (++slot_cv == R) { slot_cv = 0; phase_cv ^= 1u; }
-        if (!AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
+        if (!AHEAD) {
+            prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
+            if (mir_hi && s + 2 > Nd) row_cv[(NF + DIR)*kWY] = -row_cv[(NF + DIR)*kWY];    // (rows < 0: prologue)
+        }
         off += uss;
         weno.load(a, s);
         // VISC == 2: the x gradients of the velocities (planes [0][v] of k_vgrad) of cells s-1 and s of
@@ -1193,7 +1213,10 @@ __global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRI
             }
             const double *L = BC4 ? Ls : P.vR;
             double vs[ND];
-            if (AHEAD) prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
+            if (AHEAD) {
+                prim_in_place<NF, ND, kWY>(row_cv, a.gammas, a.pi_infs);
+                if (mir_hi && s + 3 > Nd) row_cv[(NF + DIR)*kWY] = -row_cv[(NF + DIR)*kWY];
+            }
             hllc<NF, ND, DIR>(L, vL, a.gammas, a.pi_infs, Nx.F, Nx.uf, vs);
             if (VISC == 1 && on && s >= s0) store_visc_face<NF, ND>(a, off, L, vL, vs);   // face s-1/2, left cell s-1
             if (VISC == 2) {                           // viscous source flux of face s-1/2, folded into Fn
@@ -1249,8 +1272,9 @@ __global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRI
                 }
             }
             if (next_issue <= r_last) {
+                const int rs = next_issue > Nd ? hi_a + hi_b*next_issue : next_issue;   // (rows < 0: prologue)
                 mbar_expect_tx(&bar[slot_lo], kRowBytes);
-                tma_load_row(ring + slot_lo*SLOT, &a.tm_q, cx, DIR == 1 ? cy + next_issue : cy, DIR == 1 ? cz : cz + next_issue, &bar[slot_lo]);
+                tma_load_row(ring + slot_lo*SLOT, &a.tm_q, cx, DIR == 1 ? cy + rs : cy, DIR == 1 ? cz : cz + rs, &bar[slot_lo]);
             }
         }
         next_issue++;

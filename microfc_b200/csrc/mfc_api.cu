@@ -84,6 +84,7 @@ struct Sim {
     cudaEvent_t ev_xdone[kMaxPieces] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_pre = nullptr;
     bool xp_pending = false;
+    bool bc_map = true;                // y / z ghost rows of physical boundaries synthesised by the march (no k_bc)
     bool visc_overlap = false;         // viscous fused path: y halo in flight under the x sweep of the inner rows
     double *state[3] = {nullptr, nullptr, nullptr};
     int cur = 0;                       // which buffer holds q_cons_ts(1)
@@ -285,8 +286,11 @@ void xpiece_range(int p, int &k0, int &nk, int &z0, int &nz, long long &idx0, lo
         idx0 = (long long)g.b*k0; cnt = (long long)g.b*nk;
     }
 }
-int physical_bc_dir(double *q, int d) {
+// mapped = this call is on behalf of an inviscid sweep along d: for d >= 1 the march synthesises the
+// ghost rows of physical boundaries itself (SweepArgs::map_beg / map_end) and no kernel is launched
+int physical_bc_dir(double *q, int d, bool mapped = false) {
     if (S.bc[d][0] >= 0 && S.bc[d][1] >= 0) return 0;
+    if (mapped && d >= 1 && S.bc_map && !S.viscous) return 0;
     BcArgs a{S.g, q, d, S.E, S.nf + d, S.bc[d][0], S.bc[d][1]};
     Scope sc(KC_BC); sc.done(S.L->bc(a, S.st));
     return 0;
@@ -300,13 +304,13 @@ int physical_bc_dir(double *q, int d) {
 //     are independent.  They are enqueued on the communication stream in the order x, y, z; the
 //     sweep along d waits for exchange d only (ghosts_ready), i.e. the y and z exchanges run
 //     under the x sweep.  Interior results are identical to the sequential order bit for bit.
-int ghosts_begin(double *q) {
+int ghosts_begin(double *q, bool mapped = false) {
     for (int d = 0; d < 3; d++) S.halo_pending[d] = false;
     if (!S.overlap) {
         for (int d = 0; d < S.nd; d++) {
             int rc;
             if ((S.bc[d][0] >= 0 || S.bc[d][1] >= 0) && (rc = exchange_dir(q, d, S.st))) return rc;
-            if ((rc = physical_bc_dir(q, d))) return rc;
+            if ((rc = physical_bc_dir(q, d, mapped))) return rc;
         }
         return 0;
     }
@@ -331,10 +335,10 @@ int ghosts_begin(double *q) {
     return 0;
 }
 // ghosts of direction d complete on the compute stream (overlapped mode; no-op otherwise)
-int ghosts_ready(double *q, int d) {
+int ghosts_ready(double *q, int d, bool mapped = false) {
     if (!S.overlap) return 0;
     if (S.halo_pending[d]) { CK(cudaStreamWaitEvent(S.st, S.ev_halo[d], 0)); S.halo_pending[d] = false; }
-    return physical_bc_dir(q, d);
+    return physical_bc_dir(q, d, mapped);
 }
 int fill_ghosts(double *q) {
     int rc;
@@ -426,7 +430,7 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         CK(cudaStreamWaitEvent(S.cs, S.ev_q, 0));
         if ((rc = exchange_dir(q, 1, S.cs))) return rc;
         CK(cudaEventRecord(S.ev_halo[1], S.cs));
-    } else if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q))) return rc;
+    } else if ((rc = need_all ? fill_ghosts(q) : ghosts_begin(q, true))) return rc;
     // :445-447 (fused into the sweeps; the viscous kernels read the velocity planes -- the in-sweep
     // viscous path only needs them for the cross-direction gradients, i.e. not in 1-D)
     if (S.viscous && (!S.visc_fused || stop) && (rc = run_prim(q))) return rc;
@@ -489,7 +493,13 @@ int rhs_stage(double *q, int rk_mode, const double *q1, double *qout, double dt,
         // their width, ~12 % of a 512-cell row, against ~0.2 ms of exposed x exchange at 512^3)
         const bool split_x = d == 0 && S.overlap && S.xsplit_on && S.halo_pending[0] && S.nd >= 2;
         const bool pieces_x = d == 0 && (S.xp_pending || vo);
-        if (!split_x && !pieces_x && !(vo && d == 1) && (rc = ghosts_ready(q, d))) return rc;
+        const bool mapped = !need_all;
+        a.map_beg = a.map_end = 0;
+        if (mapped && d >= 1 && S.bc_map && !S.viscous) {
+            a.map_beg = S.bc[d][0] < 0 ? S.bc[d][0] : 0;
+            a.map_end = S.bc[d][1] < 0 ? S.bc[d][1] : 0;
+        }
+        if (!split_x && !pieces_x && !(vo && d == 1) && (rc = ghosts_ready(q, d, mapped))) return rc;
         {
             const TensorMap *tq = state_tmap(q, d == 0 ? 0 : 1), *t1 = state_tmap(q1, d == 0 ? 0 : 1);
             if (!tq || !t1) return fail(MFC_B200_ESTATE, "stage state is not one of the library's state buffers");
@@ -809,6 +819,10 @@ int mfc_b200_init(const mfc_b200_params_t *p) {
         const char *e = std::getenv("MFC_B200_GRAPH");
         const long long cells = (long long)(S.g.N[0] + 1)*(S.g.N[1] + 1)*(S.g.N[2] + 1);
         S.graph_on = e ? e[0] != '0' : cells < (4LL << 20);
+    }
+    {
+        const char *e = std::getenv("MFC_B200_BCMAP");         // 0: fill the y / z ghost rows with k_bc (A/B measurements)
+        S.bc_map = !(e && e[0] == '0');
     }
     S.cur = 0; S.launches = 0; S.inited = true; S.uploaded = false; S.last_q = nullptr;
     S.err.clear();
