@@ -238,7 +238,9 @@ def parity_note(workload: str):
     fp = os.path.join(ROOT, "profiles", "r02_fast_build_linf.txt")
     if os.path.exists(fp):
         for line in open(fp):
-            w = line.split()
+            w = line.lstrip(".F").split()                # pytest's progress dots precede the printed line
+            if len(w) >= 8 and w[0] == "ASTLINF":
+                w[0] = "FASTLINF"
             if len(w) >= 8 and w[0] == "FASTLINF" and w[1] in rel:
                 note.setdefault("fast_build", {})[w[1]] = {"linf": float(w[3]), "linf_per_variable": float(w[5]), "test_bound": float(w[7]),
                                                            "oracle_1ulp_sensitivity": float(w[9]) if len(w) >= 10 else None}
@@ -451,7 +453,7 @@ def main():
     cells_gpu = ncell_total // args.gpus
     dom_flops = sweep_flops_per_cell(E, nd, dom == last_dir) * cells_gpu
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r02_v5_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_v7_traffic.json")
     if not os.path.exists(tp):
         tp = os.path.join(ROOT, "profiles", "r01_v4_traffic.json")
     if os.path.exists(tp) and nd == 3 and E == 8:

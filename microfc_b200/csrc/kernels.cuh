@@ -462,6 +462,9 @@ __device__ __forceinline__ void visc_flux_fd(const SweepArgs &a, const double *L
     F[EN] += e;
 }
 
+// pull the line of p into L2 (no register, no scoreboard): issued one iteration before the load
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void load_coef(const SweepArgs &a, int cell, double c[27]) {
     const double *p = a.coef + (cell - a.coef_lo);
 #pragma unroll
@@ -967,6 +970,7 @@ __global__ void __launch_bounds__(32*kWarpsX, (COEF == 1 && WO == 5 && !MFC_STRI
             for (int v = 0; v < ND; v++) {
                 const double *pl = a.vgrad + (size_t)(ND + v)*g.fstride + off;
                 vg_l[v] = __ldg(pl); vg_r[v] = __ldg(pl + 1);
+                prefetch_l2(pl + 32);                  // the next chunk's cells (same row, except at a wrap)
             }
         }
         double vL[E], vR[E];
@@ -1187,6 +1191,8 @@ __global__ void __launch_bounds__(32*kWarpsY, (COEF == 1 && WO == 5 && !MFC_STRI
             for (int v = 0; v < ND; v++) {
                 const double *pl = a.vgrad + (size_t)v*g.fstride + off;
                 vg_l[v] = __ldg(pl); vg_r[v] = __ldg(pl + uss);
+                prefetch_l2(pl + 2*uss);               // row s+1, read by the next iteration: DRAM latency
+                                                       // (~0.7 us) is longer than the ~0.5 us between load and use
             }
         }
         double vL[E];
