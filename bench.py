@@ -348,6 +348,17 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # a second, gloo group: ranks that wait for rank 0's CPU baseline block in a socket there instead of
+    # spinning in an NCCL barrier on cores the OpenMP threads of the baseline want
+    cpu_group = None
+    if dist is not None:
+        try:
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")          # one node: the loopback interface always exists
+            cpu_group = dist.new_group(backend="gloo")
+        except Exception as e:                                         # fall back to the NCCL barrier
+            print(f"[bench] no gloo group ({e}); waiting ranks will spin", file=sys.stderr)
+            cpu_group = None
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -489,7 +500,10 @@ def main():
         sample = args.cpu_sample_cells or {3: 128, 2: 1024, 1: 400}[nd]
         r = cpu_reference_run(cfg, 3, 1, sample)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    barrier()
+    if cpu_group is not None:
+        dist.barrier(group=cpu_group)
+    else:
+        barrier()
 
     if rank == 0:
         line = {"metric": "Mcell-steps/s", "value": value, "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": K,
