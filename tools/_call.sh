@@ -1,7 +1,4 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29811 bench.py --gpus 2 --steps 4 --warmup 3 > gpurun_out/r2_c19_bench2.json 2> gpurun_out/r2_c19_bench2.err
-tail -3 gpurun_out/r2_c19_bench2.err | cut -c1-300
-python - <<'PY'
-import json
-d = json.load(open("gpurun_out/r2_c19_bench2.json"))
-print(d["n_gpus"], round(d["value"], 1), round(d["ms_per_step"], 3), d["cpu_baseline"], d["e2e"]["value"])
-PY
+python -m pytest tests -m gpu -q > gpurun_out/r2_c20_tests.log 2>&1; tail -3 gpurun_out/r2_c20_tests.log | cut -c1-200
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python bench.py > gpurun_out/r02_v8_bench_512cube.json 2> gpurun_out/r2_c20_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/r02_v8_bench_512cube.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel'], d['roofline']['traffic'], d['e2e']['value'], d['cpu_baseline']['value'], d['gpu_launches'])"
