@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 #define MFC_B200_MAX_FLUIDS 4     /* array extents of the ABI structs (num_fluids_max is 10 in the reference) */
-#define MFC_B200_BUILT_FLUIDS 2   /* sweep kernels are instantiated for num_fluids = 1, 2 (every shipped example);
+#define MFC_B200_BUILT_FLUIDS 3   /* sweep kernels are instantiated for num_fluids = 1, 2, 3 (the shipped examples use 1 and 2);
                                      mfc_b200_init fails with MFC_B200_EUNSUPPORTED above that */
 #define MFC_B200_ABI_VERSION 1
 

@@ -29,6 +29,8 @@ UNITS = [
     # (source, extra flags)
     ("kernels_fast.cu", []),
     ("kernels_strict.cu", ["-fmad=false"]),
+    ("kernels_fast_nf3.cu", []),
+    ("kernels_strict_nf3.cu", ["-fmad=false"]),
     ("mfc_api.cu", ["-Xcompiler", "-fvisibility=default"]),
     ("weno_coefficients.cpp", ["-Xcompiler", "-ffp-contract=off"]),
     ("patches.cu", ["-fmad=false"]),
@@ -71,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return r.stderr
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=4) as ex:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             for out in ex.map(run, jobs):
                 if verbose and out:
                     print(out)

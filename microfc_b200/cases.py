@@ -98,6 +98,27 @@ def advection_2d(N: int = 99, Nt: int = 1000) -> Dict:
     }
 
 
+def three_fluids(d: Dict, gamma3: float = 1.0 / (1.3 - 1.0), pi_inf3: float = 0.0) -> Dict:
+    """A THREE-fluid variant of a two-fluid case (no reference example has more than two fluids; the
+    reference allows up to num_fluids_max = 10): a third ideal gas joins with volume fraction 0.2 taken
+    from fluid 1 in the background patch and 0.3 in every later patch, partial densities to match."""
+    out = dict(d)
+    out['num_fluids'] = 3
+    out['fluid_pp(3)%gamma'], out['fluid_pp(3)%pi_inf'] = gamma3, pi_inf3
+    for i in range(1, d['num_patches'] + 1):
+        share = 0.2 if i == 1 else 0.3
+        a1 = d.get(f'patch_icpp({i})%alpha(1)', 0.0)
+        a2 = d.get(f'patch_icpp({i})%alpha(2)', 0.0)
+        donor = 1 if a1 >= a2 else 2
+        big = max(a1, a2)
+        out[f'patch_icpp({i})%alpha(3)'] = share * big
+        out[f'patch_icpp({i})%alpha({donor})'] = big - share * big
+        rho_d = d.get(f'patch_icpp({i})%alpha_rho({donor})', 0.0)
+        out[f'patch_icpp({i})%alpha_rho(3)'] = 0.5 * share * rho_d
+        out[f'patch_icpp({i})%alpha_rho({donor})'] = rho_d - share * rho_d
+    return out
+
+
 def _shockbubble_common(dx: float, leng: float, vel: float):
     ps = 248758.567
     c_l = math.sqrt(1.4 * ps / 1.)

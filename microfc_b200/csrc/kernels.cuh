@@ -1360,6 +1360,7 @@ __device__ __forceinline__ long long bc_cell(const GridDesc &g, int dir, int s, 
     return dir == 0 ? g.at(s, t0, t1) : (dir == 1 ? g.at(t0, s, t1) : g.at(t0, t1, s));
 }
 
+#ifndef MFC_NF3_UNIT   // non-template kernels: defined once per build, in the main compile unit
 __global__ void __launch_bounds__(256) k_bc(const __grid_constant__ BcArgs a) {
     const GridDesc &g = a.g;
     const long long n = slab_count(g, a.dir);
@@ -1409,6 +1410,7 @@ __global__ void __launch_bounds__(256) k_halo_unpack(const __grid_constant__ Hal
     const int dst = a.side == 0 ? -g.b + layer : N + 1 + layer;    // ghost layers in ascending order
     a.q[(long long)v*g.fstride + bc_cell(g, a.dir, dst, t0, t1)] = a.buf[(long long)v*a.cnt + loc];
 }
+#endif  // MFC_NF3_UNIT
 
 // ------------------------------------------------------------------------------------------
 // stability criteria, m_data_output.fpp:197-258: per-cell ICFL (+VCFL, Rc when viscous), warp

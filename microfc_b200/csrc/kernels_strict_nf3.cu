@@ -1,0 +1,4 @@
+// strict build (-fmad=false), sweep kernels of num_fluids = 3 (see kernels_inst.inc: MFC_NF3_UNIT)
+#define MFC_STRICT 1
+#define MFC_NF3_UNIT
+#include "kernels_inst.inc"

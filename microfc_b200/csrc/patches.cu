@@ -163,6 +163,9 @@ int launch_patches(int nf, int nd, const PatchArgs &a, cudaStream_t st) {
     case 21: k_patches<2, 1><<<grid, 128, 0, st>>>(a); return 1;
     case 22: k_patches<2, 2><<<grid, 128, 0, st>>>(a); return 1;
     case 23: k_patches<2, 3><<<grid, 128, 0, st>>>(a); return 1;
+    case 31: k_patches<3, 1><<<grid, 128, 0, st>>>(a); return 1;
+    case 32: k_patches<3, 2><<<grid, 128, 0, st>>>(a); return 1;
+    case 33: k_patches<3, 3><<<grid, 128, 0, st>>>(a); return 1;
     default: return 0;
     }
 }

@@ -147,12 +147,12 @@ def test_init_rejects_bad_parameters_like_s_check_input_file(mutate, msg):
 
 def test_more_fluids_than_the_kernels_are_built_for_fail_at_init():
     """MFC_B200_MAX_FLUIDS (4) is the array extent of the ABI; the sweep kernels are instantiated
-    for MFC_B200_BUILT_FLUIDS (2).  Three fluids must be refused by mfc_b200_init, not by the
+    for 1..MFC_B200_BUILT_FLUIDS (3).  Four fluids must be refused by mfc_b200_init, not by the
     first step after a multi-gigabyte upload."""
     cfg = cases.config(cases.sod_1d())
     p, keep = _params(cfg, pre_process.generate_grid(cfg))
-    p.num_fluids, p.sys_size = 3, 2 * 3 + 1 + 1
-    for i in range(3):
+    p.num_fluids, p.sys_size = 4, 2 * 4 + 1 + 1
+    for i in range(4):
         p.gammas[i], p.pi_infs[i] = 2.5, 0.0
     L = abi.lib()
     assert L.mfc_b200_init(C.byref(p)) == -7               # MFC_B200_EUNSUPPORTED

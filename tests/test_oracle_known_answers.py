@@ -551,3 +551,41 @@ def test_kapila_water_air_shock_tube_matches_exact_riemann_solution():
     assert abs(x[i_shock] - (0.7 + S * T)) < 3 * dx
     i_contact = np.where(q[4][0, 0] > 0.5)[0].max()                # alpha_water = 1/2
     assert abs(x[i_contact] - (0.7 + us * T)) < 2 * dx
+
+
+# ---- three fluids ------------------------------------------------------------------------------
+def test_three_fluids_with_two_identical_gases_reduce_to_the_two_fluid_solution():
+    """Pins num_fluids = 3 in the oracle (no reference example has three fluids): fluid 3 has the
+    equation of state of fluid 1 and takes the same share s of fluid 1 everywhere, so alpha_3 rho_3 =
+    s X and alpha_1 rho_1 = (1 - s) X are proportional fields.  The mixture rules
+    (m_variables_conversion.fpp:187-227) then see the rho, Gamma, Pi of the two-fluid case, and WENO's
+    nonlinear weights are scale-invariant up to weno_eps, so total density, momenta and energy follow
+    the two-fluid run and alpha_1 + alpha_3 follows its alpha_1 (to ~1e-9: weno_eps breaks the scale
+    invariance where beta ~ 1e-16)."""
+    s_share = 0.25
+    d2 = cases.shockbubble_2d(Ny=40)
+    d3 = dict(d2)
+    d3['num_fluids'] = 3
+    d3['fluid_pp(3)%gamma'], d3['fluid_pp(3)%pi_inf'] = d2['fluid_pp(1)%gamma'], d2['fluid_pp(1)%pi_inf']
+    for i in range(1, d2['num_patches'] + 1):
+        a1, r1 = d2[f'patch_icpp({i})%alpha(1)'], d2[f'patch_icpp({i})%alpha_rho(1)']
+        d3[f'patch_icpp({i})%alpha(3)'], d3[f'patch_icpp({i})%alpha_rho(3)'] = s_share * a1, s_share * r1
+        d3[f'patch_icpp({i})%alpha(1)'], d3[f'patch_icpp({i})%alpha_rho(1)'] = a1 - s_share * a1, r1 - s_share * r1
+    out = []
+    for d in (d2, d3):
+        cfg = dataclasses.replace(cases.config(d), t_step_stop=40)
+        cb = pre_process.generate_grid(cfg)
+        o = oracle_lib.Oracle(cfg, cb)
+        o.set_q(pre_process.generate_initial_condition(cfg, cb))
+        oracle_lib.run_p_main(o, cfg)
+        out.append(o.get_q())
+    q2, q3 = out
+    rho2, rho3 = q2[0] + q2[1], q3[0] + q3[1] + q3[2]
+    tol = 1e-9
+    assert np.abs(rho3 - rho2).max() <= tol * np.abs(rho2).max()
+    for k in range(3):                                           # mom_x, mom_y, E
+        a, b = q2[2 + k], q3[3 + k]
+        assert np.abs(b - a).max() <= tol * max(np.abs(a).max(), 1.0)
+    assert np.abs((q3[6] + q3[8]) - q2[5]).max() <= tol           # alpha_1 + alpha_3 == alpha_1 of the two-fluid run
+    assert np.abs(q3[7] - q2[6]).max() <= tol
+    assert np.abs(q3[2] - s_share / (1 - s_share) * q3[0]).max() <= tol * np.abs(q3[0]).max()   # the share is advected unchanged
