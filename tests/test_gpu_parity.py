@@ -38,6 +38,12 @@ CASES = {
     "viscous_wave_2d_fd": lambda: (cases.viscous_wave_2d(weno_Re_flux=False), cases.viscous_wave_state),
     "viscous_wave_2d_weno_extrap_y": lambda: (cases.viscous_wave_2d(weno_Re_flux=True, bc_y=-6), cases.viscous_wave_state),
     "viscous_wave_2d_fd_extrap_y": lambda: (cases.viscous_wave_2d(weno_Re_flux=False, bc_y=-6), cases.viscous_wave_state),
+    # the smallest grids s_check_input_file admits (m + 1 >= 5 weno_order, m_start_up.fpp:147-229): rows
+    # shorter than one chunk of the x stream, pencils shorter than one segment of the march
+    "sod_1d_25_cells": lambda: dict(cases.sod_1d(Nx=24), dt=1e-3),
+    "advection_2d_25x25": lambda: cases.advection_2d(N=24),
+    "shockbubble_3d_25x26x27": lambda: cases.shockbubble_3d(ncx=25, ncy=26, ncz=27),
+    "vacuum_1d_weno3_15_cells": lambda: dict(cases.vacuum_1d(Nx=14)),
     # lower reconstruction orders and RK1 / RK2 (examples/1D_vacuum uses WENO3)
     "vacuum_1d_weno3": lambda: cases.vacuum_1d(),
     "sod_1d_weno1_rk1": lambda: dict(cases.sod_1d(), weno_order=1, time_stepper=1),
