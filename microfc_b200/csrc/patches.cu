@@ -94,9 +94,9 @@ template <int NF, int ND>
 __global__ void __launch_bounds__(128) k_patches(const __grid_constant__ PatchArgs a) {
     constexpr int E = 2*NF + ND + 1, MOM = NF, EN = NF + ND, ADV = NF + ND + 1;
     const GridDesc &g = a.g;
-    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    const int j = blockIdx.y*blockDim.x + threadIdx.x;
     if (j > g.N[0]) return;
-    const int k = blockIdx.y, l = blockIdx.z;
+    const int k = blockIdx.x % (g.N[1] + 1), l = blockIdx.x/(g.N[1] + 1);   // rows in gridDim.x: no 65535 cap
     const double X = a.cc[0][j], Y = ND > 1 ? a.cc[1][k] : 0.0, Z = ND > 2 ? a.cc[2][l] : 0.0;
     double q[E];
 #pragma unroll
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128) k_patches(const __grid_constant__ PatchAr
 
 int launch_patches(int nf, int nd, const PatchArgs &a, cudaStream_t st) {
     const GridDesc &g = a.g;
-    dim3 grid((g.N[0] + 128)/128, g.N[1] + 1, g.N[2] + 1);
+    dim3 grid((g.N[1] + 1)*(g.N[2] + 1), (g.N[0] + 128)/128, 1);
     switch (nf*10 + nd) {
     case 11: k_patches<1, 1><<<grid, 128, 0, st>>>(a); return 1;
     case 12: k_patches<1, 2><<<grid, 128, 0, st>>>(a); return 1;
