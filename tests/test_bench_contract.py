@@ -45,6 +45,32 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "32^3" in cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["value"] > 0
+    # the CPU arm runs a SAMPLE of the workload: its config says what was run, not the full size
+    assert j["config"]["cells_total"] == 32 ** 3 and "134217728 cells" in j["config"]["sample_of"]
+    assert abs(j["ms_per_step"] * 1e-3 * j["value"] * 1e6 - 32 ** 3) < 1e-3 * 32 ** 3
+
+
+def test_strong_scaling_splits_one_grid_by_the_reference_rule():
+    """--scaling strong: ONE global grid whatever N; the decomposition is the reference's
+    (m_mpi_proxy.fpp:163-203: 4096^2 on 8 ranks -> 4 x 2 blocks of 1024 x 2048)."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    fd = os.dup(1)                                   # importing bench.py points stdout at stderr: undo it afterwards
+    try:
+        bench = importlib.import_module("bench")
+    finally:
+        os.dup2(fd, 1)
+        os.close(fd)
+    from microfc_b200.domain import processor_topology, rank_layout
+    for n, topo, local in ((1, (1, 1, 1), (4096, 4096)), (2, (2, 1, 1), (2048, 4096)), (4, (2, 2, 1), (2048, 2048)), (8, (4, 2, 1), (1024, 2048))):
+        cfg, desc, _ = bench.workload_case("shockbubble_2d_4096", n, None, True)
+        assert (cfg.m + 1, cfg.n + 1) == (4096, 4096) and "strong" in desc
+        assert processor_topology(n, cfg) == topo
+        lay = rank_layout(0, n, cfg)
+        assert (lay.N[0] + 1, lay.N[1] + 1) == local
+    # weak scaling keeps the per-GPU size
+    cfg, _, topo = bench.workload_case("shockdroplet_2d_viscous_2048", 8, None, False)
+    assert (cfg.m + 1, cfg.n + 1) == (8192, 4096) and processor_topology(8, cfg) == (4, 2, 1) == topo
 
 
 def test_reference_arm_only_rank_zero_prints_under_torchrun():
