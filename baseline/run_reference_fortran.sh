@@ -5,7 +5,11 @@
 # `--impl reference` arm then times the C++ restatement under oracle/ instead
 # (cpu_baseline.kind = "port").
 #
-#   baseline/run_reference_fortran.sh <reference-tree> <case.py> [ranks]
+#   baseline/run_reference_fortran.sh <reference-tree> <case.py> [ranks] [--fixtures]
+#
+# --fixtures: also turn the run's restart files into tests/golden/ref_<case>.npz
+# (baseline/make_reference_fixtures.py), which pins the oracle and the CUDA path against the
+# reference itself (tests/test_reference_fixtures.py).
 #
 # Output: one line "ranks seconds_per_step grind_ns_per_cell_eq_rhs" from time_data.dat
 # (mean cpu_time per RK step over steps >= 4, max over ranks: m_time_steppers.fpp:352-358,
@@ -14,6 +18,8 @@ set -euo pipefail
 REF=${1:-/root/reference}
 CASE=${2:-$REF/examples/2D_advection/case.py}
 RANKS=${3:-$(nproc)}
+FIXTURES=${4:-}
+HERE=$(cd "$(dirname "$0")" && pwd)
 missing=()
 command -v gfortran >/dev/null 2>&1 || command -v nvfortran >/dev/null 2>&1 || missing+=("Fortran compiler (gfortran >= 5 or nvfortran)")
 command -v mpirun >/dev/null 2>&1 || missing+=("MPI (mpirun + mpif90)")
@@ -40,3 +46,6 @@ nd = 1 + (case.get("n", 0) > 0) + (case.get("p", 0) > 0)
 E = 2 * case["num_fluids"] + nd + 1
 print(ranks, secs, float(secs) / (cells * E * 3) * 1e9)
 PY
+if [ "$FIXTURES" = "--fixtures" ]; then
+    python3 "$HERE/make_reference_fixtures.py" "$CASE" --case-dir "$(dirname "$TD")"
+fi
