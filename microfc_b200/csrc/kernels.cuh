@@ -12,7 +12,7 @@
 //   m_mpi_proxy.fpp:490-499,592-601 (+y) pack / unpack       -> k_halo_pack / k_halo_unpack
 //   m_variables_conversion.fpp:313-375 cons -> prim          -> k_prim
 //   m_weno.fpp:470-535 + m_riemann_solvers.fpp:132-327 +
-//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_xstream (x: warp-shuffle stream)
+//   m_rhs.fpp:565-653 + m_time_steppers.fpp:298-348          -> k_xstream (x: cell stream through smem rings)
 //                                                               k_march3 (y / z: marching pencils)
 //   m_data_output.fpp:197-258 stability criteria             -> k_stability
 #pragma once
