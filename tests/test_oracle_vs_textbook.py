@@ -21,6 +21,9 @@ CASES = {
     "shearlayer_2d": lambda: cases.shearlayer_2d(Nx=79, Ny=39),         # periodic x, bc_y -5
     "shockdroplet_2d": lambda: cases.shockdroplet_2d(Nx=199, Ny=59),    # reflective y, water/air
     "three_fluids_2d": lambda: cases.three_fluids(cases.shockbubble_2d(Ny=40)),
+    # the 3-D EXTENSION (the reference is 1-D/2-D): the oracle's direction-by-direction generalisation
+    "shockbubble_3d": lambda: cases.shockbubble_3d(ncx=30, ncy=28, ncz=26),
+    "shockbubble_3d_periodic_z": lambda: cases.shockbubble_3d(nc=26, periodic_z=True),
 }
 
 
@@ -36,13 +39,14 @@ def test_rhs_and_steps_agree_with_the_textbook_scheme(name):
     tb = _textbook(cfg, cb)
     o = oracle_lib.Oracle(cfg, cb)
     o.set_q(q0)
-    rhs_o = o.compute_rhs(0)[:, 0]
-    rhs_t = tb.rhs(q0[:, 0])
+    drop = (slice(None), 0) if cfg.num_dims < 3 else (slice(None),)      # 1-D / 2-D arrays carry a z axis of length 1
+    rhs_o = o.compute_rhs(0)[drop]
+    rhs_t = tb.rhs(q0[drop])
     nf, nd = cfg.num_fluids, cfg.num_dims
     diff = np.abs(rhs_t - rhs_o).reshape(cfg.sys_size, -1).max(axis=1)
     scale = np.abs(rhs_o).reshape(cfg.sys_size, -1).max(axis=1)
     scale[nf:nf + nd] = scale[nf:nf + nd].max()
-    qmax = np.abs(q0[:, 0]).reshape(cfg.sys_size, -1).max(axis=1)
+    qmax = np.abs(q0).reshape(cfg.sys_size, -1).max(axis=1)
     qmax[nf:nf + nd] = max(qmax[nf:nf + nd].max(), 1e-300)
     # Per variable: the two RHS agree to 1e-11 of the RHS's own scale -- or, where the RHS is the small
     # difference of large fluxes (a nearly uniform flow: the rounding of p ~ 1e5 fluxes shows at 1e-8 of
@@ -54,9 +58,10 @@ def test_rhs_and_steps_agree_with_the_textbook_scheme(name):
     ok = (diff <= 1e-11 * scale) | (cfg.dt * diff <= per_step * qmax)
     assert ok.all(), (diff / np.where(scale == 0, 1.0, scale), cfg.dt * diff / qmax)
     q_o, _ = oracle_run(cfg, cb, q0)
-    q_t = q0[:, 0].copy()
+    q_t = q0[drop].copy()
     for _ in range(20):
         q_t = tb.step(q_t, cfg.dt)
     # water/air: the cancellation in p = (E - ...)/Gamma amplifies the rounding differences
     tol = 1e-9 if max(cfg.pi_inf[:cfg.num_fluids]) > 0 else 1e-11
-    assert (norm_linf(q_t[:, None], q_o, cfg) <= tol).all(), norm_linf(q_t[:, None], q_o, cfg)
+    q_t = q_t.reshape(q_o.shape)
+    assert (norm_linf(q_t, q_o, cfg) <= tol).all(), norm_linf(q_t, q_o, cfg)

@@ -14,7 +14,7 @@ algorithms rather than from the reference's source structure:
 The reference evaluates the same scheme through grid-dependent coefficient arrays
 (m_weno.fpp:168-363) that reduce to these constants on uniform grids only up to rounding, so the
 oracle and this file agree to ~1e-13, not bitwise: tests/test_oracle_vs_textbook.py gates at 1e-11.
-Vectorised numpy over (variable, y, x); uniform grids; boundary codes <= -3 (extrapolation),
+Vectorised numpy over (variable, [z,] y, x); uniform grids; boundary codes <= -3 (extrapolation),
 -1 (periodic), -2 (reflective).  TEST INFRASTRUCTURE: a second pin of the oracle, used nowhere else."""
 import numpy as np
 
@@ -112,11 +112,11 @@ class Textbook:
         return F, uf
 
     def rhs(self, q):
-        """q: (E, Ny, Nx) interior cells -> dq/dt."""
+        """q: (E, [Nz,] Ny, Nx) interior cells -> dq/dt."""
         nf, nd, E, b = self.nf, self.nd, self.E, 3
         out = np.zeros_like(q)
         for d in range(nd):
-            axis = 2 - d                                 # x is the last axis
+            axis = q.ndim - 1 - d                        # x is the last axis
             qg = _pad(q, b, axis, self.bc[d][0], self.bc[d][1], nf + d)
             w = self.primitive(qg)
             vL, vR = _weno5(w, axis, self.eps)           # cells -1 .. N+1
