@@ -24,12 +24,18 @@ CASES = {
     # the 3-D EXTENSION (the reference is 1-D/2-D): the oracle's direction-by-direction generalisation
     "shockbubble_3d": lambda: cases.shockbubble_3d(ncx=30, ncy=28, ncz=26),
     "shockbubble_3d_periodic_z": lambda: cases.shockbubble_3d(nc=26, periodic_z=True),
+    # viscous terms (weno_Re_flux = F: central differences): Navier-Stokes stress with shear and bulk
+    # viscosity, different Reynolds numbers per fluid, every component active
+    "viscous_wave_2d": lambda: (cases.viscous_wave_2d(weno_Re_flux=False), cases.viscous_wave_state),
+    "viscous_wave_2d_extrap_y": lambda: (cases.viscous_wave_2d(weno_Re_flux=False, bc_y=-6), cases.viscous_wave_state),
+    "shockdroplet_2d_viscous": lambda: cases.shockdroplet_2d(Nx=199, Ny=59, viscous=True),
 }
 
 
 def _textbook(cfg, cb):
     dx = [float(cb[d][1] - cb[d][0]) for d in range(cfg.num_dims)]
-    return Textbook(cfg.num_fluids, cfg.num_dims, cfg.gamma, cfg.pi_inf, dx, cfg.bc, cfg.weno_eps)
+    return Textbook(cfg.num_fluids, cfg.num_dims, cfg.gamma, cfg.pi_inf, dx, cfg.bc, cfg.weno_eps,
+                    Re=cfg.Re if cfg.viscous else None)
 
 
 @pytest.mark.parametrize("name", list(CASES))

@@ -56,12 +56,19 @@ def _weno5(v, axis, eps):
 
 
 class Textbook:
-    def __init__(self, nf, nd, gammas, pi_infs, dx, bc, eps=1e-16):
+    def __init__(self, nf, nd, gammas, pi_infs, dx, bc, eps=1e-16, Re=None):
         """gammas / pi_infs in the reference's convention: Gamma_i = 1/(gamma_i - 1),
-        Pi_i = gamma_i pi_inf_i/(gamma_i - 1).  dx[d]: uniform cell width; bc[d] = (beg, end)."""
+        Pi_i = gamma_i pi_inf_i/(gamma_i - 1).  dx[d]: uniform cell width; bc[d] = (beg, end).
+        Re[f] = (shear, bulk) Reynolds numbers of fluid f (<= 0: that fluid has none): Navier-Stokes stress
+        tau = (grad u + grad u^T - 2/3 div u I)/Re_shear + div u I/Re_bulk with the mixture rule
+        1/Re = sum_f alpha_f/Re_f, central differences, 1-D / 2-D (the reference's weno_Re_flux = F branch)."""
         self.nf, self.nd, self.E = nf, nd, 2 * nf + nd + 1
         self.G, self.P = np.asarray(gammas[:nf], float), np.asarray(pi_infs[:nf], float)
         self.dx, self.bc, self.eps = dx, bc, eps
+        self.iRe = None
+        if Re is not None and any(r > 0 for f in Re[:nf] for r in f):
+            self.iRe = np.array([[1.0 / Re[f][i] if Re[f][i] > 0 else 0.0 for f in range(nf)] for i in range(2)])
+            self.has = [any(Re[f][i] > 0 for f in range(nf)) for i in range(2)]
 
     def mixture(self, ar, al):
         rho = ar.sum(axis=0)
@@ -109,12 +116,62 @@ class Textbook:
         FK[nf + nd] = u * (En + p)
         F = FK + s * (Us - U)
         uf = u + s * (xi - 1.0)                          # velocity that advects the volume fractions
-        return F, uf
+        vs = W[nf:nf + nd].copy()                        # face velocity: upwind tangential components,
+        vs[n] = uf                                       # contact-weighted normal component
+        return F, uf, vs
+
+    def _viscous_flux(self, F, L, R, vs, w2, d, q_shape):
+        """Subtract the viscous stress of every face of direction d from the flux F (momenta) and its
+        work from the energy flux.  w2: primitive variables on the grid padded by 3 in every direction."""
+        nf, nd, b = self.nf, self.nd, 3
+        al_L, al_R = L[nf + nd + 1:], R[nf + nd + 1:]
+        iRe = [0.5 * (np.maximum(np.tensordot(self.iRe[i], al_L, axes=1), 1e-16) +
+                      np.maximum(np.tensordot(self.iRe[i], al_R, axes=1), 1e-16)) for i in range(2)]
+        ax = w2.ndim - 1 - d                             # axis of direction d in w2 (variable axis first)
+        n = q_shape[ax]
+        vel = w2[nf:nf + nd]
+
+        def faces_of(a):                                 # cells -1 .. N along d at interior transverse indices -> pairs
+            idx = [slice(None)] * a.ndim
+            for dd in range(nd):
+                axd = a.ndim - 1 - dd
+                idx[axd] = slice(b - 1, b + n + 1) if dd == d else slice(b, a.shape[axd] - b)
+            c = a[tuple(idx)]
+            lo = np.take(c, np.arange(0, n + 1), axis=ax)
+            hi = np.take(c, np.arange(1, n + 2), axis=ax)
+            return lo, hi
+        grad = [[None] * nd for _ in range(nd)]          # grad[dd][v] = d vel_v / d x_dd at the faces
+        for v in range(nd):
+            lo, hi = faces_of(vel[v][None])
+            grad[d][v] = ((hi - lo) / self.dx[d])[0]
+            for dd in range(nd):
+                if dd == d:
+                    continue
+                axd = vel[v].ndim - 1 - dd
+                central = (np.roll(vel[v], -1, axis=axd) - np.roll(vel[v], 1, axis=axd)) / (2.0 * self.dx[dd])
+                lo, hi = faces_of(central[None])
+                grad[dd][v] = (0.5 * (lo + hi))[0]
+        div = sum(grad[v][v] for v in range(nd))
+        for i in range(nd):                              # tau_{d i}
+            tau = 0.0
+            if self.has[0]:
+                tau = tau + (grad[d][i] + grad[i][d] - (2.0 / 3.0 * div if i == d else 0.0)) * iRe[0]
+            if self.has[1] and i == d:
+                tau = tau + div * iRe[1]
+            F[nf + i] = F[nf + i] - tau
+            F[nf + nd] = F[nf + nd] - vs[i] * tau
+        return F
 
     def rhs(self, q):
         """q: (E, [Nz,] Ny, Nx) interior cells -> dq/dt."""
         nf, nd, E, b = self.nf, self.nd, self.E, 3
         out = np.zeros_like(q)
+        w2 = None
+        if self.iRe is not None:                         # ghosts in every direction, x first (corners)
+            q2 = q
+            for d in range(nd):
+                q2 = _pad(q2, b, q.ndim - 1 - d, self.bc[d][0], self.bc[d][1], nf + d)
+            w2 = self.primitive(q2)
         for d in range(nd):
             axis = q.ndim - 1 - d                        # x is the last axis
             qg = _pad(q, b, axis, self.bc[d][0], self.bc[d][1], nf + d)
@@ -122,7 +179,10 @@ class Textbook:
             vL, vR = _weno5(w, axis, self.eps)           # cells -1 .. N+1
             n = q.shape[axis]
             sl = lambda a, lo, hi: np.take(a, np.arange(lo, hi), axis=axis)
-            F, uf = self.hllc(sl(vR, 0, n + 1), sl(vL, 1, n + 2), d)       # faces -1/2 .. N+1/2
+            L, R = sl(vR, 0, n + 1), sl(vL, 1, n + 2)
+            F, uf, vs = self.hllc(L, R, d)               # faces -1/2 .. N+1/2
+            if w2 is not None:
+                F = self._viscous_flux(F, L, R, vs, w2, d, q.shape)
             dF = sl(F, 0, n) - sl(F, 1, n + 1)
             out += dF / self.dx[d]
             al = q[nf + nd + 1:]
