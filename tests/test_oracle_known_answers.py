@@ -203,6 +203,38 @@ def test_weno_polynomial_exactness_on_a_stretched_grid():
         assert all(x > 0 for x in beta)
 
 
+def test_weno_beta_on_a_stretched_grid_is_the_jiang_shu_integral():
+    """On a NON-uniform grid the smoothness indicator of candidate k must be Jiang & Shu's definition
+    beta_k = sum_{l=1,2} int_cell h^(2l-1) (d^l p_k / dx^l)^2 dx for the quadratic p_k whose cell averages
+    match the three cells of the stencil: pins beta_coef (m_weno.fpp:283-345) where the uniform-grid
+    constants say nothing."""
+    cfg = cases.config(cases.sod_1d(Nx=39))
+    rng = np.random.default_rng(5)
+    w = 1.0 + 0.6 * rng.random(cfg.m + 1)
+    cbx = np.concatenate([[0.0], np.cumsum(w)])
+    cbx /= cbx[-1]
+    o = oracle_lib.Oracle(cfg, [cbx])
+    c = o.weno_coefficients(0, 0)
+    cb_g, _, _ = o.rank_metrics(0, 0)
+    b = cfg.buff_size
+    lo = -b + 2
+    left, right = cb_g[:-1], cb_g[1:]
+    v = rng.random(len(left))
+
+    def integral(cells, j):
+        A = [[(right[q] ** (p + 1) - left[q] ** (p + 1)) / ((p + 1) * (right[q] - left[q])) for p in range(3)] for q in cells]
+        a = np.linalg.solve(np.array(A), v[list(cells)])           # p(x) = a0 + a1 x + a2 x^2
+        xl, xr = left[j], right[j]
+        h = xr - xl
+        return (h * (a[1] ** 2 * (xr - xl) + 2 * a[1] * a[2] * (xr ** 2 - xl ** 2) + 4 * a[2] ** 2 * (xr ** 3 - xl ** 3) / 3)
+                + h ** 3 * 4 * a[2] ** 2 * (xr - xl))
+    for cell in range(lo + 1, cfg.m + b - 2):
+        j = cell + b
+        _, _, beta = _reconstruct(c, v, j, lo + b)
+        want = [integral((j, j + 1, j + 2), j), integral((j - 1, j, j + 1), j), integral((j - 2, j - 1, j), j)]
+        assert np.allclose(beta, want, rtol=1e-9, atol=1e-14), (cell, beta, want)
+
+
 def test_weno_beta_uniform_grid_matches_classical_formula():
     cfg, cb, _ = setup_case(cases.sod_1d(Nx=31), n_steps=1)
     o = oracle_lib.Oracle(cfg, cb)
