@@ -25,6 +25,11 @@ derived independently of any implementation:
      the advection equation, so a UNIFORM volume fraction stays uniform in a compressing flow
  14. examples/1D_kapilashocktube (water | air, stiffened gas) against the exact two-material
      Riemann solution: star pressure and velocity, contact and shock positions, density in L1
+ 15. stretched grids: the smoothness indicators are Jiang & Shu's integral definition for the
+     quadratic through the stencil's cell averages (beta_coef, m_weno.fpp:283-345)
+ 16. three fluids: a third fluid that duplicates the first reproduces the two-fluid solution
+(tests/test_oracle_vs_textbook.py adds the structurally independent pin: a textbook-form numpy
+statement of the whole scheme, inviscid and viscous, 1-D to 3-D.)
 """
 import dataclasses
 
